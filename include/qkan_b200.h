@@ -1,0 +1,113 @@
+/* qkan_b200.h - C ABI of the B200-native batched QKANLayer.forward.
+ *
+ * The reference (javiergonzalez10upf/QKAN_Implementation) is pure Python and has no FFI;
+ * each entry point below names the reference interface it stands in for
+ * (paths relative to QKAN_Steps_original/).  Plain pointers and sizes only - no torch
+ * types cross this boundary.  Every function returns QKAN_OK (0) or a negative
+ * qkan_status; nothing throws.  qkan_last_error() gives the message of the last failure
+ * on the calling thread.  See INTEGRATION.md for the ctypes binding a maintainer of the
+ * reference would add.
+ */
+#ifndef QKAN_B200_H
+#define QKAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QKAN_OK = 0,
+    QKAN_ERR_BAD_SHAPE = -1,     /* N, K < 1, D < 0, B < 0, null pointers                      */
+    QKAN_ERR_UNSUPPORTED = -2,   /* no kernel for this (N, K, D, dtype, mode): D > 31, ...     */
+    QKAN_ERR_WEIGHT_RANGE = -3,  /* some |w| > 1 (MulStep.py:36-37 raises ValueError)          */
+    QKAN_ERR_CUDA = -4,          /* CUDA runtime / launch failure, message in qkan_last_error  */
+    QKAN_ERR_NO_WEIGHTS = -5     /* forward before set_weights                                  */
+} qkan_status;
+
+/* amplitude representation of the simulated statevector */
+#define QKAN_COMPLEX128 0   /* default: complex double                                          */
+#define QKAN_COMPLEX64 1    /* complex float (inputs stay float64)                               */
+#define QKAN_REAL64 2       /* real double: every gate of the circuit is real, imag == 0 exactly */
+
+/* term polynomial */
+#define QKAN_MODE_COMPAT 0  /* reference semantics: T_D(x) for every LCU term (MulStep.py:20,59) */
+#define QKAN_MODE_PAPER 1   /* T_d(x) for term d                                                 */
+
+/* state preparation */
+#define QKAN_PREP_ANALYTIC 1 /* H^(x)(m+l)|0> written in closed form (default)                   */
+#define QKAN_PREP_GATES 0    /* start from |0...0>, run the initial Hadamards as passes          */
+
+typedef struct qkan_layer qkan_layer;   /* one QKANLayer(N, K, max_degree) on one device */
+
+/* QKANLayer.__init__ (QKANLayer.py:13-28).  device = CUDA ordinal. */
+int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree, int dtype, int mode, int prep, int device);
+void qkan_layer_destroy(qkan_layer* layer);
+
+/* MulStep.set_weights for all degrees at once (MulStep.py:24-39; called from
+ * QKANLayer.forward, QKANLayer.py:124-125).  W is float64 [max_degree+1, N*K] row-major;
+ * on_device != 0: W is a device pointer on the layer's device, else a host pointer.
+ * validate != 0: returns QKAN_ERR_WEIGHT_RANGE if any |w| > 1 (synchronises the stream).
+ * Builds the device rotation tables used by every later forward. */
+int qkan_layer_set_weights(qkan_layer* layer, const double* W, int on_device, int validate, void* cuda_stream);
+
+/* QKANLayer.forward (QKANLayer.py:77-135) over a batch, device pointers.
+ *   x    float64 [B, N] row-major                      (values outside [-1,1] are clipped,
+ *                                                        ChebyshevStep.py:52, and counted)
+ *   out  float64 [B, K]
+ *   amps optional (may be NULL): post-selected amplitudes [B, K], complex double for
+ *        QKAN_COMPLEX128 / QKAN_REAL64, complex float for QKAN_COMPLEX64.
+ * Asynchronous on cuda_stream (a cudaStream_t, NULL = default stream). */
+int qkan_layer_forward(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps, void* cuda_stream);
+
+/* Same call with HOST buffers (pinned memory recommended): the batch is cut in chunks and
+ * H2D copy, kernel and D2H copy of consecutive chunks overlap on three streams.
+ * Synchronous: returns when `out` (and `amps`) are complete. */
+int qkan_layer_forward_host(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps);
+
+/* Number of x entries seen outside [-1-1e-8, 1+1e-8] since the last call (the reference
+ * prints them, ChebyshevStep.py:46-49).  Synchronises the device; resets the counter. */
+int qkan_layer_out_of_range(qkan_layer* layer, uint64_t* count);
+
+/* Diagonals of QKANLayer.get_intermediate_matrices (QKANLayer.py:52-66) for a batch, device
+ * pointers, any output may be NULL:  cheb [B, N*K] = diag of create_dilated_chebyshev
+ * (ChebyshevStep.py:55-65), weighted [B, D+1, N*K] = diag of get_weighted_polynomial_matrix
+ * (MulStep.py:41-72), lcu [B, N*K] = diag of get_combined_matrix (LCUStep.py:18-37). */
+int qkan_layer_diagonals(qkan_layer* layer, const double* x, int64_t B, double* cheb, double* weighted,
+                         double* lcu, void* cuda_stream);
+
+/* Description of the kernel the layer resolved to, and its work per sample. */
+typedef struct {
+    int n_a, n_b, l;            /* register sizes: ceil(log2 N), ceil(log2 K), ceil(log2 (D+1)) */
+    int qubits;                 /* l + 2 + n_a + n_b                                             */
+    int tile_qubits;            /* qubits of the on-chip tile; the rest are enumerated sectors  */
+    int tile_na, tile_nb;       /* a / b qubits inside the tile                                  */
+    int local_qubits;           /* T: amplitudes per thread = 2^T                                */
+    int threads_per_cta, samples_per_cta, stages;
+    int grid, smem_bytes;       /* of the most recent launch (0 before the first)                */
+    int sectors_total, sectors_run;
+    double flops_alg;           /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)            */
+    double flops_exec;          /* what the kernel executes: 6 (3 if real) * 2^tile_qubits *
+                                   sectors_run * passes_exec                                     */
+    int passes_alg, passes_exec;
+    double io_bytes;            /* 8 N + 8 K (+ 16 K or 8 K with amps)                           */
+} qkan_kernel_info;
+int qkan_layer_info(qkan_layer* layer, qkan_kernel_info* info);
+
+/* One-shot convenience in the shape SURVEY.md 8(b) proposes: device pointers, builds (and
+ * caches per thread) a layer, sets weights without validation, runs forward. */
+int qkan_forward(const void* x, const void* w, void* out, int64_t B, int N, int K, int D,
+                 int dtype, int mode, void* amps, void* cuda_stream);
+
+/* Measured peaks used as roofline denominators: dependent-free FMA chains on every SM.
+ * fp64 != 0: DFMA, else FFMA.  Returns TFLOP/s (2 flops per FMA). */
+int qkan_measure_fma_peak(int device, int fp64, double* tflops);
+
+const char* qkan_last_error(void);
+void qkan_version(int* major, int* minor, int* patch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QKAN_B200_H */

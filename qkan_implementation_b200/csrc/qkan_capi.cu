@@ -1,0 +1,394 @@
+// qkan_capi.cu - C ABI (include/qkan_b200.h): layer handle, weight tables, kernel selection,
+// device and host-buffer forward, FMA peak microbenchmark.
+#include "qkan_kernel.cuh"
+#include "qkan_instances.h"
+#include "../../include/qkan_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace qkan;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(QKAN_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                  \
+    do {                                                          \
+        cudaError_t _e = (call);                                  \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);       \
+    } while (0)
+
+const std::vector<KernelInfo>& registry() {
+    static std::vector<KernelInfo> reg;
+    static std::once_flag once;
+    std::call_once(once, [] { qkan_register_all(reg); });
+    return reg;
+}
+
+int clog2(int n) {
+    int r = 0;
+    while ((1 << r) < n) ++r;
+    return r;
+}
+
+constexpr int MAX_CHUNKS = 16;
+
+}  // namespace
+
+struct qkan_layer {
+    int N, K, D, NA, NB, L;
+    int dtype, mode, prep, device, sm_count;
+    const KernelInfo* kern = nullptr;
+    void* wtab = nullptr;
+    int* xidx = nullptr;
+    unsigned long long* counters = nullptr;   // [0] out-of-range x, [1] |w| > 1
+    double* W_dev = nullptr;
+    bool weights_set = false;
+    int last_grid = 0, last_smem = 0;
+    // host-buffer path
+    double* d_x = nullptr;
+    double* d_out = nullptr;
+    void* d_amps = nullptr;
+    int64_t cap_x = 0, cap_out = 0, cap_amps = 0;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
+};
+
+static size_t amp_real_size(int dtype) { return dtype == QKAN_COMPLEX64 ? 4 : 8; }
+
+extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree, int dtype, int mode, int prep,
+                                 int device) {
+    if (!out) return fail(QKAN_ERR_BAD_SHAPE, "null output handle");
+    *out = nullptr;
+    if (N < 1 || K < 1) return fail(QKAN_ERR_BAD_SHAPE, "N and K must be >= 1");
+    if (max_degree < 0) return fail(QKAN_ERR_BAD_SHAPE, "Degree must be positive integer.");   // ChebyshevStep.py:14-15
+    if (dtype < 0 || dtype > 2 || mode < 0 || mode > 1 || prep < 0 || prep > 1)
+        return fail(QKAN_ERR_BAD_SHAPE, "bad dtype / mode / prep");
+    const int NA = clog2(N), NB = clog2(K), L = clog2(max_degree + 1);
+    const KernelInfo* best = nullptr;
+    for (const KernelInfo& k : registry()) {
+        if (k.amp != dtype || k.mode != mode || k.prep != prep || k.L != L || k.NAT > NA || k.NBT > NB) continue;
+        if (!best) { best = &k; continue; }
+        const int a = k.NAT + k.NBT, b = best->NAT + best->NBT;
+        if (k.prio > best->prio || (k.prio == best->prio && (a > b || (a == b && k.NBT > best->NBT)))) best = &k;
+    }
+    if (!best) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "no sm_100a kernel for N=%d K=%d D=%d (l=%d) dtype=%d mode=%d prep=%d", N, K,
+                 max_degree, L, dtype, mode, prep);
+        return fail(QKAN_ERR_UNSUPPORTED, buf);
+    }
+    CU(cudaSetDevice(device));
+    qkan_layer* l = new qkan_layer();
+    l->N = N; l->K = K; l->D = max_degree; l->NA = NA; l->NB = NB; l->L = L;
+    l->dtype = dtype; l->mode = mode; l->prep = prep; l->device = device;
+    l->kern = best;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete l; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    l->sm_count = prop.multiProcessorCount;
+    const size_t nab = (size_t)1 << (NA + NB);
+    e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
+    if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nab * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&l->counters, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(l->counters, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&l->W_dev, (size_t)(max_degree + 1) * N * K * sizeof(double));
+    if (e != cudaSuccess) { qkan_layer_destroy(l); return cuda_fail(e, "cudaMalloc(layer tables)"); }
+    *out = l;
+    return QKAN_OK;
+}
+
+extern "C" void qkan_layer_destroy(qkan_layer* l) {
+    if (!l) return;
+    cudaSetDevice(l->device);
+    cudaFree(l->wtab); cudaFree(l->xidx); cudaFree(l->counters); cudaFree(l->W_dev);
+    cudaFree(l->d_x); cudaFree(l->d_out); cudaFree(l->d_amps);
+    if (l->s_in) cudaStreamDestroy(l->s_in);
+    if (l->s_k) cudaStreamDestroy(l->s_k);
+    if (l->s_out) cudaStreamDestroy(l->s_out);
+    for (int i = 0; i < MAX_CHUNKS; ++i) {
+        if (l->ev_in[i]) cudaEventDestroy(l->ev_in[i]);
+        if (l->ev_k[i]) cudaEventDestroy(l->ev_k[i]);
+    }
+    delete l;
+}
+
+extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_device, int validate, void* cuda_stream) {
+    if (!l || !W) return fail(QKAN_ERR_BAD_SHAPE, "null layer or weights");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    CU(cudaSetDevice(l->device));
+    const size_t nw = (size_t)(l->D + 1) * l->N * l->K;
+    if (W != l->W_dev)
+        CU(cudaMemcpyAsync(l->W_dev, W, nw * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           stream));
+    const double* Wd = l->W_dev;
+    CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
+    const unsigned nab = 1u << (l->NA + l->NB);
+    const unsigned nt = 128, nb = (nab + nt - 1) / nt;
+    if (l->dtype == QKAN_COMPLEX64)
+        qkan_prepare_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->NA, l->NB, l->L,
+                                                                 (CS<float>*)l->wtab, l->xidx, l->counters + 1);
+    else
+        qkan_prepare_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->NA, l->NB, l->L,
+                                                                  (CS<double>*)l->wtab, l->xidx, l->counters + 1);
+    CU(cudaGetLastError());
+    if (validate) {
+        unsigned long long bad = 0;
+        CU(cudaMemcpyAsync(&bad, l->counters + 1, sizeof bad, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        if (bad) {
+            l->weights_set = false;
+            return fail(QKAN_ERR_WEIGHT_RANGE, "Weight magnitudes must be <= 1 for unitarity");   // MulStep.py:37
+        }
+    }
+    l->weights_set = true;
+    return QKAN_OK;
+}
+
+static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream) {
+    LaunchParams p;
+    p.x = x; p.wtab = l->wtab; p.xidx = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
+    p.B = B; p.N = l->N; p.K = l->K; p.D = l->D; p.NA = l->NA; p.NB = l->NB;
+    p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
+    p.amp_scale = pow(2.0, -0.5 * (double)(l->NA + l->NB + 2 * l->L + l->NA));
+    p.tma_ok = 0;
+    cudaError_t e = l->kern->launch(p, l->sm_count, stream, &l->last_grid, &l->last_smem);
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_forward_kernel launch");
+    return QKAN_OK;
+}
+
+extern "C" int qkan_layer_forward(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, void* cuda_stream) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
+    CU(cudaSetDevice(l->device));
+    return launch_on(l, x, B, out, amps, (cudaStream_t)cuda_stream);
+}
+
+static int ensure_host_path(qkan_layer* l, int64_t B, bool want_amps) {
+    if (!l->s_in) {
+        CU(cudaStreamCreateWithFlags(&l->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&l->s_k, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&l->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            CU(cudaEventCreateWithFlags(&l->ev_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&l->ev_k[i], cudaEventDisableTiming));
+        }
+    }
+    if (l->cap_x < B) {
+        cudaFree(l->d_x); l->d_x = nullptr; l->cap_x = 0;
+        CU(cudaMalloc(&l->d_x, (size_t)B * l->N * sizeof(double)));
+        l->cap_x = B;
+    }
+    if (l->cap_out < B) {
+        cudaFree(l->d_out); l->d_out = nullptr; l->cap_out = 0;
+        CU(cudaMalloc(&l->d_out, (size_t)B * l->K * sizeof(double)));
+        l->cap_out = B;
+    }
+    if (want_amps && l->cap_amps < B) {
+        cudaFree(l->d_amps); l->d_amps = nullptr; l->cap_amps = 0;
+        CU(cudaMalloc(&l->d_amps, (size_t)B * l->K * 2 * amp_real_size(l->dtype)));
+        l->cap_amps = B;
+    }
+    return QKAN_OK;
+}
+
+extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B, double* out, void* amps) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
+    CU(cudaSetDevice(l->device));
+    int rc = ensure_host_path(l, B, amps != nullptr);
+    if (rc) return rc;
+    // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile
+    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 21);   // ~2 MiB of traffic per chunk
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
+    int64_t per = (B + nchunk - 1) / nchunk;
+    const int64_t spi = l->kern->spi;
+    per = (per + spi - 1) / spi * spi;
+    const size_t asz = 2 * amp_real_size(l->dtype);
+    int i = 0;
+    for (int64_t off = 0; off < B; off += per, ++i) {
+        const int64_t n = (B - off < per) ? (B - off) : per;
+        CU(cudaMemcpyAsync(l->d_x + off * l->N, x + off * l->N, (size_t)n * l->N * sizeof(double),
+                           cudaMemcpyHostToDevice, l->s_in));
+        CU(cudaEventRecord(l->ev_in[i], l->s_in));
+        CU(cudaStreamWaitEvent(l->s_k, l->ev_in[i], 0));
+        rc = launch_on(l, l->d_x + off * l->N, n, l->d_out + off * l->K,
+                       amps ? (char*)l->d_amps + (size_t)off * l->K * asz : nullptr, l->s_k);
+        if (rc) return rc;
+        CU(cudaEventRecord(l->ev_k[i], l->s_k));
+        CU(cudaStreamWaitEvent(l->s_out, l->ev_k[i], 0));
+        CU(cudaMemcpyAsync(out + off * l->K, l->d_out + off * l->K, (size_t)n * l->K * sizeof(double),
+                           cudaMemcpyDeviceToHost, l->s_out));
+        if (amps)
+            CU(cudaMemcpyAsync((char*)amps + (size_t)off * l->K * asz, (char*)l->d_amps + (size_t)off * l->K * asz,
+                               (size_t)n * l->K * asz, cudaMemcpyDeviceToHost, l->s_out));
+    }
+    CU(cudaStreamSynchronize(l->s_out));
+    return QKAN_OK;
+}
+
+extern "C" int qkan_layer_out_of_range(qkan_layer* l, uint64_t* count) {
+    if (!l || !count) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    CU(cudaSetDevice(l->device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CU(cudaMemcpy(&v, l->counters, sizeof v, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(l->counters, 0, sizeof v));
+    *count = v;
+    return QKAN_OK;
+}
+
+extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
+    if (!l || !info) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    const KernelInfo& k = *l->kern;
+    memset(info, 0, sizeof *info);
+    info->n_a = l->NA; info->n_b = l->NB; info->l = l->L;
+    info->qubits = l->L + 2 + l->NA + l->NB;
+    info->tile_na = k.NAT; info->tile_nb = k.NBT;
+    info->tile_qubits = k.L + 2 + k.NAT + k.NBT;
+    info->local_qubits = k.T;
+    info->threads_per_cta = k.NT; info->samples_per_cta = k.spi; info->stages = k.stages;
+    info->grid = l->last_grid; info->smem_bytes = l->last_smem;
+    info->sectors_total = 1 << (l->NA - k.NAT + l->NB - k.NBT);
+    const int na_run = (l->N + (1 << k.NAT) - 1) >> k.NAT, nb_run = (l->K + (1 << k.NBT) - 1) >> k.NBT;
+    info->sectors_run = na_run * nb_run;
+    info->passes_alg = (l->D + 1) + (l->NA + l->NB) + 2 * l->L + l->NA;
+    info->passes_exec = (l->D + 1) + (k.prep ? (k.L + k.NAT) : (2 * k.L + 2 * k.NAT + k.NBT));
+    info->flops_alg = 6.0 * (double)(1ll << info->qubits) * info->passes_alg;
+    info->flops_exec = (l->dtype == QKAN_REAL64 ? 3.0 : 6.0) * (double)(1ll << info->tile_qubits) *
+                       info->sectors_run * info->passes_exec;
+    info->io_bytes = 8.0 * l->N + 8.0 * l->K;
+    return QKAN_OK;
+}
+
+// per-stage diagonals (debug / verbose path): one thread per (sample, i)
+__global__ void qkan_diagonals_kernel(const double* x, const double* W, long long B, int N, int K, int D, int mode,
+                                      double* cheb, double* weighted, double* lcu) {
+    const long long NK = (long long)N * K;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * NK) return;
+    const long long s = gid / NK;
+    const int i = (int)(gid - s * NK);
+    const double xc = clip_unit<double>(x[s * N + i / K]);          // ChebyshevStep.py:52,64
+    const double th = acos(xc);
+    const double cD = cos((double)D * th);                           // ChebyshevStep.py:30
+    if (cheb) cheb[gid] = cD;
+    double acc = 0.0;
+    for (int d = 0; d <= D; ++d) {
+        const double c = mode == 0 ? cD : cos((double)d * th);
+        const double m = c * W[(long long)d * NK + i];               // MulStep.py:72
+        if (weighted) weighted[(s * (D + 1) + d) * NK + i] = m;
+        acc += m / (double)(D + 1);                                  // LCUStep.py:36
+    }
+    if (lcu) lcu[gid] = acc;
+}
+
+extern "C" int qkan_layer_diagonals(qkan_layer* l, const double* x, int64_t B, double* cheb, double* weighted,
+                                    double* lcu, void* cuda_stream) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "diagonals called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
+    CU(cudaSetDevice(l->device));
+    const long long total = (long long)B * l->N * l->K;
+    const unsigned nt = 256;
+    const unsigned nb = (unsigned)((total + nt - 1) / nt);
+    qkan_diagonals_kernel<<<nb, nt, 0, (cudaStream_t)cuda_stream>>>(x, l->W_dev, B, l->N, l->K, l->D, l->mode, cheb,
+                                                                    weighted, lcu);
+    CU(cudaGetLastError());
+    return QKAN_OK;
+}
+
+extern "C" int qkan_forward(const void* x, const void* w, void* out, int64_t B, int N, int K, int D, int dtype,
+                            int mode, void* amps, void* cuda_stream) {
+    thread_local qkan_layer* cached = nullptr;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (cached && (cached->N != N || cached->K != K || cached->D != D || cached->dtype != dtype ||
+                   cached->mode != mode || cached->device != dev)) {
+        qkan_layer_destroy(cached);
+        cached = nullptr;
+    }
+    if (!cached) {
+        int rc = qkan_layer_create(&cached, N, K, D, dtype, mode, QKAN_PREP_ANALYTIC, dev);
+        if (rc) return rc;
+    }
+    int rc = qkan_layer_set_weights(cached, (const double*)w, 1, 0, cuda_stream);
+    if (rc) return rc;
+    return qkan_layer_forward(cached, (const double*)x, B, (double*)out, amps, cuda_stream);
+}
+
+// ------------------------------------------------------------- FMA peak
+template <typename R> __global__ void __launch_bounds__(256) fma_peak_kernel(R* sink, int iters, R b, R c) {
+    R a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (R)(threadIdx.x + i) * (R)1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = qk_fma(a[i], b, c);
+        }
+    }
+    R s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == (R)123456.789) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int qkan_measure_fma_peak(int device, int fp64, double* tflops) {
+    if (!tflops) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount * 8, nt = 256, iters = fp64 ? 8192 : 16384;
+    void* sink = nullptr;
+    CU(cudaMalloc(&sink, (size_t)grid * nt * 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0));
+        if (fp64) fma_peak_kernel<double><<<grid, nt>>>((double*)sink, iters, 0.999999, 1e-6);
+        else fma_peak_kernel<float><<<grid, nt>>>((float*)sink, iters, 0.9999f, 1e-4f);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8 * 4 * (double)iters * grid * nt;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops = best;
+    return QKAN_OK;
+}
+
+extern "C" const char* qkan_last_error(void) { return g_last_error.c_str(); }
+extern "C" void qkan_version(int* major, int* minor, int* patch) {
+    if (major) *major = 0;
+    if (minor) *minor = 1;
+    if (patch) *patch = 0;
+}

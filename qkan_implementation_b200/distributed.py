@@ -1,0 +1,71 @@
+"""Batch sharding of QKANLayer.forward over the GPUs of one box.
+
+Samples are independent and the weights are shared read-only, so the path shards with no
+data-path collective: rank r of g takes the contiguous slice [r*B/g, (r+1)*B/g) (remainder
+spread over the first ranks), every rank runs the same kernel, and the only communication
+is one gather of the [B/g, K] outputs (NCCL all_gather over NVLink/NVSwitch; gloo on CPU
+for the host-logic tests).  The gathered result is bitwise equal to the single-GPU result.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(B: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous slice of rank `rank`: sizes differ by at most one, earlier ranks get the extra."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(B: int, world: int) -> List[int]:
+    return [shard_bounds(B, world, r)[1] - shard_bounds(B, world, r)[0] for r in range(world)]
+
+
+def gather_outputs(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
+    """All ranks receive the full [B, K] output.  Uneven shards are padded to the largest one
+    so a single all_gather_into_tensor moves everything."""
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(B, world)
+    mx = max(sizes) if sizes else 0
+    K = local.shape[1]
+    if local.shape[0] < mx:
+        pad = torch.zeros((mx - local.shape[0], K), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=0)
+    full = torch.empty((world * mx, K), dtype=local.dtype, device=local.device)
+    if local.is_cuda:
+        dist.all_gather_into_tensor(full, local.contiguous(), group=group)
+    else:  # gloo: list form
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local.contiguous(), group=group)
+        full = torch.cat(parts, dim=0)
+    if all(s == mx for s in sizes):
+        return full
+    return torch.cat([full[r * mx: r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+class ShardedQKANLayer:
+    """One process per GPU; `forward` takes the FULL batch description and computes this
+    rank's slice.  ``compute`` is the per-rank callable (the CUDA QKANLayer on a GPU box;
+    injectable so the sharding logic can be tested on CPU with gloo)."""
+
+    def __init__(self, layer=None, compute=None, group=None):
+        if (layer is None) == (compute is None):
+            raise ValueError("give exactly one of `layer` or `compute`")
+        self.layer = layer
+        self.compute = compute if compute is not None else (lambda x, w: layer.forward(x, w))
+        self.group = group
+
+    def forward_local(self, x_full: torch.Tensor, weights) -> Tuple[torch.Tensor, Tuple[int, int]]:
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = shard_bounds(x_full.shape[0], world, rank)
+        return self.compute(x_full[lo:hi], weights), (lo, hi)
+
+    def forward(self, x_full: torch.Tensor, weights, gather: bool = True):
+        y, _ = self.forward_local(x_full, weights)
+        if not gather:
+            return y
+        return gather_outputs(y, x_full.shape[0], self.group)

@@ -1,0 +1,133 @@
+"""CPU: the C-ABI library loads and exports every symbol include/qkan_b200.h declares; the host
+mirror of the reference API validates like the reference; batch sharding logic (gloo, 2 ranks)."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "qkan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(qkan_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from qkan_implementation_b200 import _binding
+    lib = _binding.lib()
+    names = _header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/qkan_b200.h but not exported"
+    assert set(_binding.EXPORTS) == set(names)
+    v = [ctypes.c_int() for _ in range(3)]
+    lib.qkan_version(*[ctypes.byref(i) for i in v])
+    assert (v[0].value, v[1].value) == (0, 1)
+
+
+def test_abi_argument_errors_without_gpu():
+    from qkan_implementation_b200 import _binding as b
+    lib = b.lib()
+    h = ctypes.c_void_p()
+    assert lib.qkan_layer_create(ctypes.byref(h), 0, 4, 3, 0, 0, 1, 0) == b.ERR_BAD_SHAPE
+    assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, -1, 0, 0, 1, 0) == b.ERR_BAD_SHAPE
+    assert b"positive" in lib.qkan_last_error()
+    assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, 64, 0, 0, 1, 0) == b.ERR_UNSUPPORTED   # D > 31
+    assert lib.qkan_layer_forward(None, None, 1, None, None, None) == b.ERR_BAD_SHAPE
+
+
+def test_no_cpu_fallback_when_no_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from qkan_implementation_b200 import QKANLayer, _binding
+    layer = QKANLayer(4, 4, 3)
+    with pytest.raises(_binding.QkanError):
+        layer.forward(np.zeros(4), [np.zeros(16)] * 4)
+
+
+def test_step_validation_matches_reference():
+    from qkan_implementation_b200 import ChebyshevStep, MulStep, QKANLayer
+    with pytest.raises(ValueError, match="Degree must be positive integer"):      # ChebyshevStep.py:14
+        ChebyshevStep(-1)
+    with pytest.raises(ValueError, match="between -1 and 1"):                     # ChebyshevStep.py:26
+        ChebyshevStep(1).apply_chebyshev(1.5)
+    m = MulStep(2, 4)
+    assert m._weights.shape == (3, 4) and m.num_weights == 4
+    with pytest.raises(ValueError, match="Degree must be between 0 and 2"):       # MulStep.py:32 / test :236
+        m.set_weights(3, np.zeros(4))
+    with pytest.raises(ValueError, match="Expected 4 weights, got 3"):            # MulStep.py:34 / test :176
+        m.set_weights(0, np.zeros(3))
+    with pytest.raises(ValueError, match="Weight magnitudes must be <= 1"):       # MulStep.py:36 / test :170
+        m.set_weights(0, np.array([1.5, 0, 0, 0]))
+    m.set_weights(1, np.array([1, .5, -.5, -1]))
+    assert np.array_equal(m._weights[1], [1, .5, -.5, -1])
+    with pytest.raises(ValueError, match="does not match expected size 6 = 3\\*2"):   # MulStep.py:62-66
+        m.get_weighted_polynomial_matrix(np.zeros(3), 2, 1)
+    layer = QKANLayer(4, 4, 3)
+    assert (layer.N, layer.K, layer.max_degree) == (4, 4, 3)
+    assert layer.mul_step.num_weights == 16 and layer.cheb_step.degree == 3 and layer.lcu_step.max_degree == 3
+    with pytest.raises(ValueError, match="Weight magnitudes"):
+        layer.forward(np.zeros(4), [np.full(16, 2.0)] * 4)
+    with pytest.raises(ValueError, match="Degree must be between 0 and 3"):
+        layer.forward(np.zeros(4), [np.zeros(16)] * 5)
+    with pytest.raises(ValueError, match="Expected input dimension 4, got 3"):    # QKANLayer.py:41
+        layer.get_intermediate_matrices(np.zeros(3), [np.zeros(16)] * 4)
+    with pytest.raises(ValueError, match="Expected 4 weight vectors"):            # QKANLayer.py:43
+        layer.get_intermediate_matrices(np.zeros(4), [np.zeros(16)] * 3)
+    with pytest.raises(ValueError, match="Expected weight dimension 16"):         # QKANLayer.py:48
+        layer.get_intermediate_matrices(np.zeros(4), [np.zeros(15)] * 4)
+
+
+def test_shard_bounds_cover_batch():
+    from qkan_implementation_b200.distributed import shard_bounds, shard_sizes
+    for B in (0, 1, 7, 8, 1000, 10_000_001):
+        for g in (1, 2, 4, 8):
+            edges = [shard_bounds(B, g, r) for r in range(g)]
+            assert edges[0][0] == 0 and edges[-1][1] == B
+            assert all(edges[r][1] == edges[r + 1][0] for r in range(g - 1))
+            sz = shard_sizes(B, g)
+            assert max(sz) - min(sz) <= 1 and sum(sz) == B
+
+
+def _gloo_worker(rank, world, port, B, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import qkan_oracle as o
+    from qkan_implementation_b200.distributed import ShardedQKANLayer
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    N, K, D = 4, 4, 3
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.uniform(-1, 1, (B, N)))
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    compute = lambda xs, w: torch.from_numpy(o.forward_closed_form(xs.numpy(), w, N, K, D)) if xs.shape[0] else torch.zeros((0, K), dtype=torch.float64)
+    sh = ShardedQKANLayer(compute=compute)
+    full = sh.forward(x, W)
+    ref = torch.from_numpy(o.forward_closed_form(x.numpy(), W, N, K, D))
+    q.put((rank, bool(torch.equal(full, ref)), tuple(full.shape)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B", [10, 11, 1])
+def test_sharded_forward_gloo_world2(B):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (B, 4) for _, _, shape in res)

@@ -1,0 +1,39 @@
+"""CPU: the kernel's compile-time stage plans, swizzle and read-out (qkan_core.cuh compiled with
+g++ and run group-by-group) against the oracle.  Config ids are listed in tests/emu/qkan_emu.cpp;
+id + 100 = the same tile with the initial Hadamards executed as gates."""
+import numpy as np
+import pytest
+
+from oracle import qkan_oracle as o
+
+CASES = {0: (4, 4, 3), 1: (4, 4, 3), 2: (4, 4, 3), 3: (4, 4, 3), 4: (4, 4, 3), 5: (4, 4, 3), 6: (4, 4, 3),
+         7: (4, 4, 3), 8: (16, 16, 8), 9: (16, 16, 8), 10: (8, 8, 16), 11: (8, 8, 1), 12: (3, 2, 4),
+         13: (5, 3, 1), 14: (1, 1, 0), 15: (784, 10, 5), 16: (8, 8, 5), 17: (8, 8, 5), 18: (2, 2, 1),
+         19: (4, 4, 10)}
+PAPER = (7, 17)
+C64 = (5,)
+
+
+@pytest.mark.parametrize("prep_gates", [0, 1])
+@pytest.mark.parametrize("cfg", sorted(CASES))
+def test_emulated_kernel_matches_oracle(emu, cfg, prep_gates):
+    N, K, D = CASES[cfg]
+    rng = np.random.default_rng(cfg)
+    B = 2 if N > 100 else 5
+    x = rng.uniform(-1, 1, (B, N))
+    x[0, 0] = 1.3 if N > 1 else 0.2          # clipped
+    if B > 2:
+        x[1] = 0.0
+        x[2] = 1.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    out = np.zeros((B, K))
+    amps = np.zeros((B, K, 2))
+    rc = emu.qkan_emu_forward(cfg + 100 * prep_gates, x.ctypes.data, W.ctypes.data, B, N, K, D,
+                              out.ctypes.data, amps.ctypes.data)
+    assert rc == 0
+    ref = o.forward_closed_form(x, W, N, K, D, "paper" if cfg in PAPER else "compat")
+    tol = 1e-5 if cfg in C64 else 1e-14
+    assert np.abs(out - ref).max() <= tol
+    spec = o.circuit_spec(N, K, D)
+    assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
+    assert np.abs(amps[..., 1]).max() == 0.0

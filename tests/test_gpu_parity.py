@@ -1,0 +1,259 @@
+"""GPU: the CUDA path, called through the C ABI (ctypes) and the drop-in Python layer, against
+ (1) golden vectors produced by the unmodified reference, (2) the CPU oracle on seeded inputs,
+ (3) size-independent properties at BASELINE.json's full batch sizes.
+Tolerances (BASELINE.json north_star): 1e-10 relative for complex128 (and the real-only
+representation), 1e-4 relative for complex64 - relative 2-norm per sample, plus an absolute
+floor for all-zero outputs (the reference's own zero-input test uses atol 1e-6)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_batches, rel_err
+from oracle import qkan_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"complex128": 1e-10, "real64": 1e-10, "complex64": 1e-4}
+ATOL = {"complex128": 1e-13, "real64": 1e-13, "complex64": 2e-6}
+
+
+def assert_close(got, ref, dtype="complex128"):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape
+    bad = np.abs(got - ref) > ATOL[dtype]
+    if bad.any():
+        g2, r2 = np.atleast_2d(got), np.atleast_2d(ref)
+        rows = np.atleast_2d(bad).any(axis=1)
+        assert rel_err(g2[rows], r2[rows]) <= RTOL[dtype], f"max abs err {np.abs(got - ref).max()}"
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import qkan_implementation_b200 as q
+    assert torch.cuda.is_available()
+    return q
+
+
+# ---------------------------------------------------------------- golden vectors
+@pytest.mark.parametrize("prep", ["analytic", "gates"])
+@pytest.mark.parametrize("dtype", ["complex128", "complex64", "real64"])
+@pytest.mark.parametrize("N,K,D,path", golden_batches())
+def test_golden_batches(Q, N, K, D, path, dtype, prep):
+    g = np.load(path)
+    layer = Q.QKANLayer(N, K, D, dtype=dtype, prep=prep)
+    out, amps = layer.forward(g["x"], list(g["W"]), return_amplitudes=True)
+    assert out.shape == g["out"].shape and out.dtype == np.float64
+    assert_close(out, g["out"], dtype)
+    spec = o.circuit_spec(N, K, D)
+    assert_close(amps.real * spec.out_scale, g["out"], dtype)
+    assert np.abs(amps.imag).max() == 0.0
+    # same call on device tensors, and one sample at a time like the reference
+    xd = torch.from_numpy(g["x"]).cuda()
+    outd = layer.forward(xd, list(g["W"]))
+    assert outd.is_cuda and np.array_equal(outd.cpu().numpy(), out)          # host path == device path, bitwise
+    one = layer.forward(g["x"][0], list(g["W"]))
+    assert one.shape == (K,) and np.array_equal(one, out[0])
+
+
+def test_kat_reference_test_vector(Q):
+    g = np.load(f"{GOLDEN}/kat_layer_4_4_3.npz")
+    layer = Q.QKANLayer(4, 4, 3)
+    W = list(g["W"])
+    assert_close(layer.forward(g["x"], W), g["out"])
+    z = layer.forward(g["x_zero"], W)
+    assert np.allclose(z, 0, atol=1e-6) and np.abs(z).max() < 1e-15            # QKANLayer.py:250-252
+    assert_close(layer.forward(g["x_boundary"], W), g["out_boundary"])
+    assert len(z) == 4 and np.all(np.abs(layer.forward(g["x"], W)) <= 1)       # QKANLayer.py:159-160
+
+
+def test_intermediate_matrices_and_verbose(Q, capsys):
+    g = np.load(f"{GOLDEN}/kat_layer_4_4_3.npz")
+    layer = Q.QKANLayer(4, 4, 3)
+    m = layer.get_intermediate_matrices(g["x"], list(g["W"]))
+    assert m["cheb"][0].shape == (16, 16) and m["weighted"][0].shape == (16, 16) and m["lcu"].shape == (16, 16)
+    for d in range(4):
+        assert np.abs(np.diag(m["cheb"][d]) - g["cheb_diag"][d]).max() <= 1e-15
+        assert np.abs(np.diag(m["weighted"][d]) - g["weighted_diag"][d]).max() <= 1e-15
+        assert np.count_nonzero(m["weighted"][d] - np.diag(np.diag(m["weighted"][d]))) == 0
+    assert np.abs(np.diag(m["lcu"]) - g["lcu_diag"]).max() <= 1e-15
+    assert np.abs(m["reshaped"] - g["reshaped"]).max() <= 1e-15
+    assert_close(m["final"], g["final"])
+    out = layer.forward(g["x"], list(g["W"]), verbose=True)
+    assert_close(out, g["out"])
+    txt = capsys.readouterr().out
+    assert "QKAN Layer Forward Pass" in txt and "Step 4 (LCU)" in txt
+    d = layer.get_intermediate_diagonals(np.stack([g["x"], g["x_boundary"]]))
+    assert d["weighted"].shape == (2, 4, 16) and np.abs(d["lcu"][0] - g["lcu_diag"]).max() <= 1e-15
+
+
+def test_step_api_known_answers(Q):
+    k = np.load(f"{GOLDEN}/kat_steps.npz")
+    assert abs(Q.ChebyshevStep(1).apply_chebyshev(0.5) - 0.5) < 1e-15           # ChebyshevStep.py:73
+    assert abs(Q.ChebyshevStep(2).apply_chebyshev(0.5) + 0.5) < 1e-15
+    assert np.abs(Q.ChebyshevStep(2).transform_diagonal(np.array([0.5, -0.5, 0.0])) - k["t2"]).max() < 1e-15
+    assert np.abs(Q.ChebyshevStep(1).create_dilated_chebyshev(np.array([0.5, -0.5]), 2) - k["dil"]).max() < 1e-15
+    ms = Q.MulStep(1, 4)
+    ms.set_weights(1, np.array([1, .5, -.5, -1]))
+    assert np.abs(ms.get_weighted_polynomial_matrix(np.array([.5, -.5]), 2, 1) - k["mul_deg1"]).max() < 1e-15
+    ms2 = Q.MulStep(2, 4)
+    ms2.set_weights(2, np.array([.5, .5, -.5, -.5]))
+    assert np.abs(ms2.get_weighted_polynomial_matrix(np.array([.5, -.5]), 2, 2) - k["mul_deg2"]).max() < 1e-15
+    lcu = Q.LCUStep(2).get_combined_matrix(np.array([.5, -.5]), ms2, 2)
+    assert np.abs(np.diag(lcu) - np.array([-.25, -.25, .25, .25]) / 3).max() < 1e-15
+
+
+def test_out_of_range_inputs_clip_and_warn(Q, capsys):
+    g = np.load(f"{GOLDEN}/clip_4_4_3.npz")
+    layer = Q.QKANLayer(4, 4, 3)
+    out = layer.forward(g["x"], list(g["W"]))
+    assert_close(out, g["out"])
+    assert "Values outside [-1,1] range" in capsys.readouterr().out            # ChebyshevStep.py:48-49
+    xd = torch.from_numpy(g["x"]).cuda()
+    layer.forward(xd, list(g["W"]))
+    n_bad = int((np.abs(g["x"]) > 1 + 1e-8).sum())
+    assert layer.out_of_range_count() == n_bad
+    assert layer.out_of_range_count() == 0                                      # counter resets
+    xn = g["x"].copy()
+    xn[0, 0] = np.nan
+    assert np.isnan(layer.forward(xn, list(g["W"]))[0]).any()                   # np.clip keeps NaN
+
+
+# ------------------------------------------------------------------- seeded oracle parity
+SHAPES = [(4, 4, 3), (4, 8, 2), (8, 4, 2), (3, 2, 4), (8, 8, 5), (5, 3, 1), (16, 16, 8), (8, 8, 1),
+          (8, 8, 2), (8, 8, 3), (8, 8, 4), (8, 8, 8), (8, 8, 16), (4, 4, 10), (4, 4, 20), (1, 1, 0),
+          (2, 2, 1), (1, 5, 2), (7, 1, 3), (33, 3, 2), (100, 10, 5), (4, 4, 31)]
+
+
+@pytest.mark.parametrize("N,K,D", SHAPES)
+def test_oracle_parity_seeded(Q, N, K, D):
+    rng = np.random.default_rng(17 * N + K + D)
+    B = 257                                   # ragged: not a multiple of any CTA tile
+    x = rng.uniform(-1, 1, (B, N))
+    x[3] = 1.0
+    x[4] = -1.0
+    x[5] = 0.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    W[0, 0] = 1.0
+    W[-1, -1] = -1.0
+    ref = o.forward_closed_form(x, W, N, K, D)
+    for dtype in ("complex128", "complex64", "real64"):
+        layer = Q.QKANLayer(N, K, D, dtype=dtype)
+        assert_close(layer.forward(x, W), ref, dtype)
+    layer = Q.QKANLayer(N, K, D, prep="gates")
+    assert_close(layer.forward(x, W), ref)
+    if N * K <= 64 and D <= 8:
+        sv, amps = o.statevector_forward(x[:16], W, N, K, D)
+        _, a = Q.QKANLayer(N, K, D).forward(x[:16], W, return_amplitudes=True)
+        assert np.abs(a - amps).max() <= 1e-14                                 # post-selected amplitudes
+
+
+@pytest.mark.parametrize("N,K,D", [(4, 4, 3), (8, 8, 5), (3, 2, 4), (5, 3, 1)])
+def test_paper_mode(Q, N, K, D):
+    rng = np.random.default_rng(N + K + D)
+    x = rng.uniform(-1, 1, (65, N))
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    layer = Q.QKANLayer(N, K, D, mode="paper")
+    assert_close(layer.forward(x, W), o.forward_closed_form(x, W, N, K, D, "paper"))
+
+
+def test_mnist_shape_single_sample(Q):
+    g = np.load(f"{GOLDEN}/batch_784_10_5.npz")
+    layer = Q.QKANLayer(784, 10, 5)
+    assert_close(layer.forward(g["x"], g["W"]), g["out"])
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, (37, 784))
+    assert_close(layer.forward(x, g["W"]), o.forward_closed_form(x, g["W"], 784, 10, 5))
+
+
+def test_empty_and_tiny_batches(Q):
+    layer = Q.QKANLayer(4, 4, 3)
+    W = np.random.default_rng(0).uniform(-1, 1, (4, 16))
+    assert layer.forward(np.zeros((0, 4)), W).shape == (0, 4)
+    assert layer.forward(torch.zeros((0, 4), dtype=torch.float64, device="cuda"), W).shape == (0, 4)
+    for B in (1, 2, 15, 16, 17, 31, 33):
+        x = np.random.default_rng(B).uniform(-1, 1, (B, 4))
+        assert_close(layer.forward(x, W), o.forward_closed_form(x, W, 4, 4, 3))
+
+
+def test_weights_are_stateful_like_reference(Q):
+    # forward(weights) overwrites mul_step._weights (QKANLayer.py:124-125 -> MulStep.py:39)
+    rng = np.random.default_rng(3)
+    layer = Q.QKANLayer(4, 4, 3)
+    x = rng.uniform(-1, 1, (8, 4))
+    W1, W2 = rng.uniform(-1, 1, (4, 16)), rng.uniform(-1, 1, (4, 16))
+    y1 = layer.forward(x, list(W1))
+    assert np.array_equal(layer.mul_step._weights, W1)
+    y2 = layer.forward(x, list(W2))
+    assert not np.array_equal(y1, y2)
+    assert_close(y2, o.forward_closed_form(x, W2, 4, 4, 3))
+    y3 = layer.forward(x, list(W1[:2]))                 # fewer rows: the rest keep their old values
+    Wm = W2.copy()
+    Wm[:2] = W1[:2]
+    assert_close(y3, o.forward_closed_form(x, Wm, 4, 4, 3))
+    # device weights: validated on the GPU
+    Wd = torch.from_numpy(W1).cuda()
+    yd = layer.forward(torch.from_numpy(x).cuda(), Wd)
+    assert np.array_equal(yd.cpu().numpy(), y1)
+    with pytest.raises(ValueError, match="Weight magnitudes"):
+        layer.forward(torch.from_numpy(x).cuda(), Wd * 3)
+
+
+# ------------------------------------------------------------------ raw C ABI
+def test_c_abi_direct(Q):
+    b = Q._binding
+    lib = b.lib()
+    N, K, D, B = 4, 4, 3, 1000
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.uniform(-1, 1, (B, N))).cuda()
+    W = torch.from_numpy(rng.uniform(-1, 1, (D + 1, N * K))).cuda()
+    out = torch.empty((B, K), dtype=torch.float64, device="cuda")
+    rc = lib.qkan_forward(x.data_ptr(), W.data_ptr(), out.data_ptr(), B, N, K, D, 0, 0, None, None)
+    assert rc == 0, lib.qkan_last_error()
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), o.forward_closed_form(x.cpu().numpy(), W.cpu().numpy(), N, K, D))
+    h = ctypes.c_void_p()
+    assert lib.qkan_layer_create(ctypes.byref(h), N, K, D, 0, 0, 1, 0) == 0
+    assert lib.qkan_layer_forward(h, x.data_ptr(), B, out.data_ptr(), None, None) == b.ERR_NO_WEIGHTS
+    assert lib.qkan_layer_set_weights(h, (W * 2).data_ptr(), 1, 1, None) == b.ERR_WEIGHT_RANGE
+    assert lib.qkan_layer_set_weights(h, W.data_ptr(), 1, 1, None) == 0
+    assert lib.qkan_layer_forward(h, x.data_ptr(), B, out.data_ptr(), None, None) == 0
+    info = b.KernelInfo()
+    assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
+    assert info.qubits == 8 and info.flops_alg == 21504 and info.grid > 0
+    lib.qkan_layer_destroy(h)
+    assert b.measure_fma_peak(0, True) > 5.0
+
+
+# ------------------------------------------------- full-size, size-independent properties
+@pytest.mark.parametrize("N,K,D,B", [(4, 4, 3, 1_000_000), (8, 8, 4, 300_000), (16, 16, 8, 20_000)])
+def test_full_size_properties(Q, N, K, D, B):
+    gen = torch.Generator().manual_seed(0)
+    x = (torch.rand((B, N), dtype=torch.float64, generator=gen) * 2 - 1)
+    W = (torch.rand((D + 1, N * K), dtype=torch.float64, generator=torch.Generator().manual_seed(1)) * 2 - 1)
+    layer = Q.QKANLayer(N, K, D)
+    xd, Wd = x.cuda(), W.cuda()
+    y = layer.forward(xd, Wd)
+    # (1) sampled rows against the oracle
+    idx = torch.randint(0, B, (4096,), generator=gen)
+    assert_close(y[idx.cuda()].cpu().numpy(), o.forward_closed_form(x[idx].numpy(), W.numpy(), N, K, D))
+    # (2) determinism and batch-slicing invariance: any slice gives bitwise the same rows
+    lo, hi = B // 3 + 1, B // 3 + 1 + 50_001 if B > 100_000 else B // 2
+    assert torch.equal(layer.forward(xd[lo:hi].contiguous(), Wd), y[lo:hi])
+    assert torch.equal(layer.forward(xd, Wd), y)
+    # (3) linearity in the weights: f(x; a W1 + b W2) = a f(x; W1) + b f(x; W2)
+    W2 = (torch.rand(W.shape, dtype=torch.float64, generator=gen) * 2 - 1).cuda()
+    ya = layer.forward(xd, 0.25 * Wd + 0.5 * W2)
+    yb = 0.25 * y + 0.5 * layer.forward(xd, W2)
+    assert float((ya - yb).abs().max()) < 1e-13
+    # (4) parity of T_D: f(-x) = (-1)^D f(x);  |out| <= 1 (QKANLayer.py:160)
+    ym = layer.forward(-xd, Wd)
+    assert float((ym - ((-1) ** D) * y).abs().max()) < 1e-13
+    assert float(y.abs().max()) <= 1.0
+    # (5) checksum against the closed form over the WHOLE batch (float64 on the GPU via torch)
+    th = torch.arccos(xd.clamp(-1, 1))
+    c = torch.cos(D * th)[:, torch.arange(N * K, device="cuda") // K]
+    ref = (c * Wd.mean(dim=0)[None, :]).reshape(B, K, N).sum(dim=2) / N
+    assert float((y - ref).abs().max()) < 1e-13

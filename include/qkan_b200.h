@@ -79,19 +79,25 @@ int qkan_layer_diagonals(qkan_layer* layer, const double* x, int64_t B, double* 
 
 /* Description of the kernel the layer resolved to, and its work per sample. */
 typedef struct {
-    int n_a, n_b, l;            /* register sizes: ceil(log2 N), ceil(log2 K), ceil(log2 (D+1)) */
-    int qubits;                 /* l + 2 + n_a + n_b                                             */
-    int tile_qubits;            /* qubits of the on-chip tile; the rest are enumerated sectors  */
-    int tile_na, tile_nb;       /* a / b qubits inside the tile                                  */
-    int local_qubits;           /* T: amplitudes per thread = 2^T                                */
-    int threads_per_cta, samples_per_cta, stages;
-    int grid, smem_bytes;       /* of the most recent launch (0 before the first)                */
-    int sectors_total, sectors_run;
-    double flops_alg;           /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)            */
-    double flops_exec;          /* what the kernel executes: 6 (3 if real) * 2^tile_qubits *
-                                   sectors_run * passes_exec                                     */
-    int passes_alg, passes_exec;
-    double io_bytes;            /* 8 N + 8 K (+ 16 K or 8 K with amps)                           */
+    int engine;                 /* 0 = block engine (prep = analytic, default); 1 = staged full-statevector
+                                   engine (prep = gates)                                                  */
+    int n_a, n_b, l, qubits;    /* register sizes ceil(log2 N), ceil(log2 K), ceil(log2 (D+1)); total     */
+    /* block engine */
+    int blocks;                 /* N*K*(D+1) live four-amplitude (f_x, f_w) blocks per sample             */
+    int unroll;                 /* U: blocks (4U amplitudes) per lane in registers                        */
+    int lanes_per_sample, lanes_per_row, rows_in_parallel, passes, row_steps;
+    /* staged engine */
+    int tile_qubits, tile_na, tile_nb, local_qubits, stages, sectors_total, sectors_run;
+    /* launch */
+    int threads_per_cta, min_ctas_per_sm, samples_per_cta;
+    int grid, smem_bytes;       /* of the most recent launch (0 before the first)                         */
+    /* work per sample */
+    int passes_survey, passes_exec;
+    double flops_survey;        /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)                     */
+    double flops_exec;          /* arithmetic the kernel executes (DFMA = 2, DMUL = DADD = 1)             */
+    double fp_inst_exec;        /* FP64 (FP32 for complex64) lane-instructions behind flops_exec          */
+    double layout_efficiency;   /* live block slots / issued block slots (block engine)                   */
+    double io_bytes;            /* 8 N + 8 K                                                              */
 } qkan_kernel_info;
 int qkan_layer_info(qkan_layer* layer, qkan_kernel_info* info);
 

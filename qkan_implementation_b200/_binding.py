@@ -27,11 +27,13 @@ EXPORTS = [
 
 class KernelInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
-                ("n_a", "n_b", "l", "qubits", "tile_qubits", "tile_na", "tile_nb", "local_qubits",
-                 "threads_per_cta", "samples_per_cta", "stages", "grid", "smem_bytes",
-                 "sectors_total", "sectors_run")] + \
-               [("flops_alg", ctypes.c_double), ("flops_exec", ctypes.c_double),
-                ("passes_alg", ctypes.c_int), ("passes_exec", ctypes.c_int), ("io_bytes", ctypes.c_double)]
+                ("engine", "n_a", "n_b", "l", "qubits",
+                 "blocks", "unroll", "lanes_per_sample", "lanes_per_row", "rows_in_parallel", "passes", "row_steps",
+                 "tile_qubits", "tile_na", "tile_nb", "local_qubits", "stages", "sectors_total", "sectors_run",
+                 "threads_per_cta", "min_ctas_per_sm", "samples_per_cta", "grid", "smem_bytes",
+                 "passes_survey", "passes_exec")] + \
+               [(n, ctypes.c_double) for n in
+                ("flops_survey", "flops_exec", "fp_inst_exec", "layout_efficiency", "io_bytes")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

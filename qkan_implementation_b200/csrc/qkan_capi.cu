@@ -1,10 +1,12 @@
 // qkan_capi.cu - C ABI (include/qkan_b200.h): layer handle, weight tables, kernel selection,
 // device and host-buffer forward, FMA peak microbenchmark.
 #include "qkan_kernel.cuh"
+#include "qkan_block.cuh"
 #include "qkan_instances.h"
 #include "../../include/qkan_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -36,6 +38,13 @@ const std::vector<KernelInfo>& registry() {
     return reg;
 }
 
+const std::vector<BlockKernelInfo>& block_registry() {
+    static std::vector<BlockKernelInfo> reg;
+    static std::once_flag once;
+    std::call_once(once, [] { qkan_register_all_block(reg); });
+    return reg;
+}
+
 int clog2(int n) {
     int r = 0;
     while ((1 << r) < n) ++r;
@@ -49,7 +58,10 @@ constexpr int MAX_CHUNKS = 16;
 struct qkan_layer {
     int N, K, D, NA, NB, L;
     int dtype, mode, prep, device, sm_count;
-    const KernelInfo* kern = nullptr;
+    int engine = 0;                           // 0 = block engine, 1 = staged full-statevector engine
+    const KernelInfo* kern = nullptr;         // staged
+    const BlockKernelInfo* bkern = nullptr;   // block
+    BlockLayout lay{};
     void* wtab = nullptr;
     int* xidx = nullptr;
     unsigned long long* counters = nullptr;   // [0] out-of-range x, [1] |w| > 1
@@ -77,30 +89,80 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         return fail(QKAN_ERR_BAD_SHAPE, "bad dtype / mode / prep");
     const int NA = clog2(N), NB = clog2(K), L = clog2(max_degree + 1);
     const KernelInfo* best = nullptr;
-    for (const KernelInfo& k : registry()) {
-        if (k.amp != dtype || k.mode != mode || k.prep != prep || k.L != L || k.NAT > NA || k.NBT > NB) continue;
-        if (!best) { best = &k; continue; }
-        const int a = k.NAT + k.NBT, b = best->NAT + best->NBT;
-        if (k.prio > best->prio || (k.prio == best->prio && (a > b || (a == b && k.NBT > best->NBT)))) best = &k;
-    }
-    if (!best) {
-        char buf[160];
-        snprintf(buf, sizeof buf, "no sm_100a kernel for N=%d K=%d D=%d (l=%d) dtype=%d mode=%d prep=%d", N, K,
-                 max_degree, L, dtype, mode, prep);
-        return fail(QKAN_ERR_UNSUPPORTED, buf);
+    const BlockKernelInfo* bbest = nullptr;
+    BlockLayout lay{};
+    if (prep == QKAN_PREP_ANALYTIC) {
+        // block engine: any N, K, D.  Pick the lane layout and the CTA size whose x tile fits.
+        if ((long long)N * K >= (1 << 20) || max_degree >= 2048)
+            return fail(QKAN_ERR_UNSUPPORTED, "block engine limits: N*K < 2^20, D < 2048");
+        const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB" (0 = any)
+        int fU = 0, fNT = 0, fMINB = 0;
+        if (tune) sscanf(tune, "%d:%d:%d", &fU, &fNT, &fMINB);
+        const size_t per_x = 8 + 2 * amp_real_size(dtype);
+        const int NTs[4] = {256, 128, 64, 32};
+        for (int ni = 0; ni < 4 && !bbest; ++ni) {
+            const int NT = NTs[ni];
+            if (fNT && NT != fNT) continue;
+            for (int min_g = 0; min_g <= 5 && !bbest; ++min_g) {
+                const BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
+                const int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
+                if (G < (1 << min_g) || G > NT) continue;
+                if ((size_t)(NT / G) * N * per_x > 72 * 1024) continue;
+                for (const BlockKernelInfo& k : block_registry()) {
+                    if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
+                    if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
+                    bbest = &k;
+                    lay = cand;
+                    break;
+                }
+            }
+        }
+        if (!bbest) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "no block kernel for N=%d K=%d D=%d dtype=%d mode=%d (input row too wide for shared memory?)",
+                     N, K, max_degree, dtype, mode);
+            return fail(QKAN_ERR_UNSUPPORTED, buf);
+        }
+    } else {
+        int best_prio = 0;
+        const char* venv = getenv("QKAN_VARIANT");          // tuning aid: prefer one variant of a tile
+        const int want_variant = venv ? atoi(venv) : -1;
+        for (const KernelInfo& k : registry()) {
+            if (k.amp != dtype || k.mode != mode || k.prep != prep || k.L != L || k.NAT > NA || k.NBT > NB) continue;
+            if (k.full && (k.NAT != NA || k.NBT != NB)) continue;
+            const int prio = k.prio + ((k.variant == want_variant) ? 100 : 0);
+            if (!best) { best = &k; best_prio = prio; continue; }
+            const int a = k.NAT + k.NBT, b = best->NAT + best->NBT;
+            if (prio > best_prio || (prio == best_prio && (a > b || (a == b && k.NBT > best->NBT)))) { best = &k; best_prio = prio; }
+        }
+        if (!best) {
+            char buf[200];
+            snprintf(buf, sizeof buf, "no staged (prep=gates) sm_100a kernel for N=%d K=%d D=%d (l=%d) dtype=%d mode=%d: "
+                     "that engine covers D <= 31, compat mode", N, K, max_degree, L, dtype, mode);
+            return fail(QKAN_ERR_UNSUPPORTED, buf);
+        }
     }
     CU(cudaSetDevice(device));
     qkan_layer* l = new qkan_layer();
     l->N = N; l->K = K; l->D = max_degree; l->NA = NA; l->NB = NB; l->L = L;
     l->dtype = dtype; l->mode = mode; l->prep = prep; l->device = device;
     l->kern = best;
+    l->bkern = bbest;
+    l->lay = lay;
+    l->engine = (prep == QKAN_PREP_ANALYTIC) ? 0 : 1;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { delete l; return cuda_fail(e, "cudaGetDeviceProperties"); }
     l->sm_count = prop.multiProcessorCount;
     const size_t nab = (size_t)1 << (NA + NB);
-    e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
-    if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nab * sizeof(int));
+    const size_t nblk = (size_t)N * K * (max_degree + 1);
+    if (l->engine == 0) {
+        e = cudaMalloc(&l->wtab, nblk * 2 * amp_real_size(dtype));
+        if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nblk * sizeof(int));
+    } else {
+        e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
+        if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nab * sizeof(int));
+    }
     if (e == cudaSuccess) e = cudaMalloc(&l->counters, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(l->counters, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&l->W_dev, (size_t)(max_degree + 1) * N * K * sizeof(double));
@@ -134,6 +196,16 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
                            stream));
     const double* Wd = l->W_dev;
     CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
+    if (l->engine == 0) {
+        const long long E = (long long)l->N * l->K * (l->D + 1);
+        const unsigned nt = 128, nb = (unsigned)((E + nt - 1) / nt);
+        if (l->dtype == QKAN_COMPLEX64)
+            qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, (CS<float>*)l->wtab, l->xidx,
+                                                                           l->counters + 1);
+        else
+            qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, (CS<double>*)l->wtab, l->xidx,
+                                                                            l->counters + 1);
+    } else {
     const unsigned nab = 1u << (l->NA + l->NB);
     const unsigned nt = 128, nb = (nab + nt - 1) / nt;
     if (l->dtype == QKAN_COMPLEX64)
@@ -142,6 +214,7 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
     else
         qkan_prepare_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->NA, l->NB, l->L,
                                                                   (CS<double>*)l->wtab, l->xidx, l->counters + 1);
+    }
     CU(cudaGetLastError());
     if (validate) {
         unsigned long long bad = 0;
@@ -157,6 +230,21 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
 }
 
 static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream) {
+    if (l->engine == 0) {
+        BlockParams p;
+        p.x = x; p.wtab = l->wtab; p.xitab = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
+        p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
+        p.rowlen = l->N * (l->D + 1);
+        p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
+        p.passes = l->lay.passes; p.brows = l->lay.brows;
+        p.sub = 1; p.tma_ok = 0;
+        p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
+        p.amp_scale = pow(2.0, -0.5 * (double)(l->NA + l->NB + 2 * l->L + l->NA));
+        cudaError_t e = l->bkern->launch(p, 1 << (l->lay.g_r_log2 + l->lay.g_k_log2), l->sm_count, stream, &l->last_grid,
+                                         &l->last_smem);
+        if (e != cudaSuccess) return cuda_fail(e, "qkan_block_kernel launch");
+        return QKAN_OK;
+    }
     LaunchParams p;
     p.x = x; p.wtab = l->wtab; p.xidx = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
     p.B = B; p.N = l->N; p.K = l->K; p.D = l->D; p.NA = l->NA; p.NB = l->NB;
@@ -220,7 +308,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     if (nchunk < 1) nchunk = 1;
     if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
     int64_t per = (B + nchunk - 1) / nchunk;
-    const int64_t spi = l->kern->spi;
+    const int64_t spi = l->engine == 0 ? (l->bkern->NT >> (l->lay.g_r_log2 + l->lay.g_k_log2)) : l->kern->spi;
     per = (per + spi - 1) / spi * spi;
     const size_t asz = 2 * amp_real_size(l->dtype);
     int i = 0;
@@ -258,24 +346,53 @@ extern "C" int qkan_layer_out_of_range(qkan_layer* l, uint64_t* count) {
 
 extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
     if (!l || !info) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
-    const KernelInfo& k = *l->kern;
     memset(info, 0, sizeof *info);
+    info->engine = l->engine;
     info->n_a = l->NA; info->n_b = l->NB; info->l = l->L;
     info->qubits = l->L + 2 + l->NA + l->NB;
-    info->tile_na = k.NAT; info->tile_nb = k.NBT;
-    info->tile_qubits = k.L + 2 + k.NAT + k.NBT;
-    info->local_qubits = k.T;
-    info->threads_per_cta = k.NT; info->samples_per_cta = k.spi; info->stages = k.stages;
     info->grid = l->last_grid; info->smem_bytes = l->last_smem;
-    info->sectors_total = 1 << (l->NA - k.NAT + l->NB - k.NBT);
-    const int na_run = (l->N + (1 << k.NAT) - 1) >> k.NAT, nb_run = (l->K + (1 << k.NBT) - 1) >> k.NBT;
-    info->sectors_run = na_run * nb_run;
-    info->passes_alg = (l->D + 1) + (l->NA + l->NB) + 2 * l->L + l->NA;
-    info->passes_exec = (l->D + 1) + (k.prep ? (k.L + k.NAT) : (2 * k.L + 2 * k.NAT + k.NBT));
-    info->flops_alg = 6.0 * (double)(1ll << info->qubits) * info->passes_alg;
-    info->flops_exec = (l->dtype == QKAN_REAL64 ? 3.0 : 6.0) * (double)(1ll << info->tile_qubits) *
-                       info->sectors_run * info->passes_exec;
+    info->passes_survey = (l->D + 1) + (l->NA + l->NB) + 2 * l->L + l->NA;
+    info->flops_survey = 6.0 * (double)(1ll << info->qubits) * info->passes_survey;
     info->io_bytes = 8.0 * l->N + 8.0 * l->K;
+    const double cf = (l->dtype == QKAN_REAL64) ? 0.5 : 1.0;      // real-only representation: half the arithmetic
+    if (l->engine == 0) {
+        const BlockKernelInfo& k = *l->bkern;
+        const int G = 1 << (l->lay.g_r_log2 + l->lay.g_k_log2);
+        info->blocks = l->N * l->K * (l->D + 1);
+        info->unroll = k.U;
+        info->lanes_per_sample = G;
+        info->lanes_per_row = 1 << l->lay.g_r_log2;
+        info->rows_in_parallel = 1 << l->lay.g_k_log2;
+        info->passes = l->lay.passes;
+        info->row_steps = l->lay.brows;
+        info->threads_per_cta = k.NT;
+        info->min_ctas_per_sm = k.MINB;
+        info->samples_per_cta = k.NT / G;
+        info->passes_exec = l->D + 1;
+        // per live block: D rotations of two complex pairs (2 x (4 DMUL + 4 DFMA) = 24 flops, 16 instructions),
+        // the SELECT rotation pruned to its (0,0) output (2 DMUL + 2 DFMA = 6 flops, 4 instructions) and one
+        // complex add into the read-out sum (2 flops, 2 instructions)
+        info->flops_exec = cf * (double)info->blocks * (24.0 * l->D + 8.0);
+        info->fp_inst_exec = cf * (double)info->blocks * (16.0 * l->D + 6.0);
+        info->layout_efficiency = l->lay.efficiency;
+    } else {
+        const KernelInfo& k = *l->kern;
+        info->tile_na = k.NAT; info->tile_nb = k.NBT;
+        info->tile_qubits = k.L + 2 + k.NAT + k.NBT;
+        info->local_qubits = k.T;
+        info->threads_per_cta = k.NT; info->samples_per_cta = k.spi; info->stages = k.stages;
+        info->sectors_total = 1 << (l->NA - k.NAT + l->NB - k.NBT);
+        const int na_run = (l->N + (1 << k.NAT) - 1) >> k.NAT, nb_run = (l->K + (1 << k.NBT) - 1) >> k.NBT;
+        info->sectors_run = na_run * nb_run;
+        const int hp = k.prep ? (k.L + k.NAT) : (2 * k.L + 2 * k.NAT + k.NBT);
+        info->passes_exec = (l->D + 1) + hp;
+        // upper bound: rotations 6 flops / 4 instructions per amplitude, un-normalised Hadamards 2 / 2; the last
+        // stage's Hadamards are pruned by the compiler to the post-selected outputs, so the real count is lower
+        const double amps_run = (double)(1ll << info->tile_qubits) * info->sectors_run;
+        info->flops_exec = cf * amps_run * (6.0 * (l->D + 1) + 2.0 * hp);
+        info->fp_inst_exec = cf * amps_run * (4.0 * (l->D + 1) + 2.0 * hp);
+        info->layout_efficiency = 1.0;
+    }
     return QKAN_OK;
 }
 

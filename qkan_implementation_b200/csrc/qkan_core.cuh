@@ -211,6 +211,11 @@ struct TileArgs {
     int NA;                 // full number of a qubits
     int a_hi, b_hi;         // sector = values of the a / b qubits above the tile
     int D;                  // number of CHEB applications (MODE 0 = compat: all terms; 1 = paper: term d gets d)
+    // direct read-out (tile = whole register): rows of out / amps of this sample, or null
+    int K;
+    double* out_row;
+    void* amp_row;
+    double out_scale, amp_scale;
 };
 
 template <typename R> QK_HD R clip_unit(double x) {
@@ -227,8 +232,76 @@ template <class P> constexpr int find_slot(const P& p, int S, int bit) {
     return -1;
 }
 
-template <class A, typename R, class P, int S, int MODE>
-QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, A* acc) {
+// Sample-independent part of the multiplexor stage, per thread: the weight rotation
+// (cos, sin) of every local control value and the x-row index feeding the input rotation.
+// Depends on the sector only, so the kernel loads it once per sector (once per launch when
+// the whole register fits the tile).
+template <typename R, class P>
+struct MuxCoef {
+    static constexpr int NC = P::T - 2;
+    R cw[1 << NC], sw[1 << NC];
+    int xi[1 << NC];
+    int dloc[1 << NC];
+
+    // local index j (flags ignored) -> compressed control index c
+    static constexpr int compress(int j) {
+        constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
+        constexpr int kx = find_slot(p, p.mstage, P::BIT_FX), kw = find_slot(p, p.mstage, P::BIT_FW);
+        int c = 0, cc = 0;
+        for (int k = 0; k < P::T; ++k) if (k != kx && k != kw) { c |= ((j >> k) & 1) << cc; ++cc; }
+        return c;
+    }
+    static constexpr unsigned expand(int c) {
+        constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
+        constexpr int kx = find_slot(p, p.mstage, P::BIT_FX), kw = find_slot(p, p.mstage, P::BIT_FW);
+        unsigned j = 0;
+        int cc = 0;
+        for (int k = 0; k < P::T; ++k) if (k != kx && k != kw) { j |= ((unsigned)(c >> cc) & 1u) << k; ++cc; }
+        return j;
+    }
+    // the x coefficient depends on (a, b) only: entry that shares it and has all deg slots = 0
+    static constexpr int ab_source(int c) {
+        constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
+        constexpr int kx = find_slot(p, p.mstage, P::BIT_FX), kw = find_slot(p, p.mstage, P::BIT_FW);
+        int cc = 0, cab = 0;
+        for (int k = 0; k < P::T; ++k) if (k != kx && k != kw) {
+            if (!is_deg(p.local[p.mstage][k], P::L)) cab |= ((c >> cc) & 1) << cc;
+            ++cc;
+        }
+        return cab;
+    }
+};
+
+template <typename R, class P>
+QK_HD void load_mux_coefs(MuxCoef<R, P>& mc, unsigned t, const TileArgs<R>& ta) {
+    constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
+    constexpr int S = p.mstage, L = P::L, NAT = P::NAT, NBT = P::NBT;
+    unsigned base = 0;
+    QK_UNROLL
+    for (int i = 0; i < P::NL; ++i) base |= ((t >> i) & 1u) << p.lane[S][i];
+    const unsigned a_thr = (base >> P::BIT_A0) & ((1u << NAT) - 1u);
+    const unsigned b_thr = (base >> P::BIT_B0) & ((1u << NBT) - 1u);
+    const unsigned d_thr = base & ((1u << L) - 1u);
+    const unsigned ab_thr = ((((unsigned)ta.b_hi << NBT) | b_thr) << ta.NA) | (((unsigned)ta.a_hi << NAT) | a_thr);
+    QK_UNROLL
+    for (int c = 0; c < (1 << MuxCoef<R, P>::NC); ++c) {
+        const unsigned dj = dep_local(p, S, MuxCoef<R, P>::expand(c));
+        const unsigned a_loc = (dj >> P::BIT_A0) & ((1u << NAT) - 1u);
+        const unsigned b_loc = (dj >> P::BIT_B0) & ((1u << NBT) - 1u);
+        const unsigned d_loc = dj & ((1u << L) - 1u);
+        const unsigned ab = ab_thr + (b_loc << ta.NA) + a_loc;
+        const CS<R> w = ta.wtab[(ab << L) | d_thr | d_loc];
+        mc.cw[c] = w.c;
+        mc.sw[c] = w.s;
+        mc.dloc[c] = (int)(d_thr | d_loc);
+        mc.xi[c] = ta.xidx[ab];
+    }
+}
+
+// DIRECT: the tile is the whole register, so the post-selected amplitudes of the last stage go
+// straight from registers to global memory (otherwise they are summed over sectors in `acc`).
+template <class A, typename R, class P, int S, int MODE, bool DIRECT = false>
+QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, const MuxCoef<R, P>& mc, A* acc) {
     constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
     constexpr int T = P::T, NLOC = 1 << T, L = P::L, NAT = P::NAT, NBT = P::NBT, FW = P::FW;
     constexpr bool last = (S == p.ns - 1), mux = (S == p.mstage);
@@ -263,50 +336,17 @@ QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, A* acc) {
 
     // ---- multiplexor passes
     if constexpr (mux) {
-        // slots of f_x / f_w and of the local control qubits
         constexpr int kx = find_slot(p, S, P::BIT_FX);
         constexpr int kw = find_slot(p, S, P::BIT_FW);
         static_assert(kx >= 0 && kw >= 0, "M stage must hold both flag qubits");
         constexpr int NC = T - 2;                 // local control slots (all non-flag slots)
-        // thread part of the control values
-        const unsigned a_thr = (base >> P::BIT_A0) & ((1u << NAT) - 1u);
-        const unsigned b_thr = (base >> P::BIT_B0) & ((1u << NBT) - 1u);
-        const unsigned d_thr = base & ((1u << L) - 1u);
-        const unsigned ab_thr = ((((unsigned)ta.b_hi << NBT) | b_thr) << ta.NA) | (((unsigned)ta.a_hi << NAT) | a_thr);
-
-        // control-slot compression: c in [0, 2^NC) enumerates the local control slots in order
-        R cx[1 << NC], sx[1 << NC], cw[1 << NC], sw[1 << NC];
-        int dloc[1 << NC];
+        // x coefficients of this sample: cos(theta_x/2) = clip(x), sin = sqrt(1 - x^2) (no acos needed)
+        R cx[1 << NC], sx[1 << NC];
         QK_UNROLL
         for (int c = 0; c < (1 << NC); ++c) {
-            // expand c -> local index j with flags = 0
-            unsigned j = 0;
-            {
-                int cc = 0;
-                for (int k = 0; k < T; ++k) if (k != kx && k != kw) { j |= ((c >> cc) & 1u) << k; ++cc; }
-            }
-            const unsigned dj = dep_local(p, S, j);
-            const unsigned a_loc = (dj >> P::BIT_A0) & ((1u << NAT) - 1u);
-            const unsigned b_loc = (dj >> P::BIT_B0) & ((1u << NBT) - 1u);
-            const unsigned d_loc = dj & ((1u << L) - 1u);
-            const unsigned ab = ab_thr + (b_loc << ta.NA) + a_loc;
-            const CS<R> w = ta.wtab[(ab << L) | d_thr | d_loc];
-            cw[c] = w.c; sw[c] = w.s;
-            dloc[c] = (int)(d_thr | d_loc);
-            // x coefficient only depends on (a, b): reuse the value of the entry with d_loc = 0
-            bool fresh = true;
-            int src = c;
-            {
-                // find an earlier c' with the same a/b local bits (differs only in deg slots)
-                int cc = 0; unsigned cab = 0;
-                for (int k = 0; k < T; ++k) if (k != kx && k != kw) {
-                    if (!is_deg(p.local[S][k], L)) cab |= ((c >> cc) & 1u) << cc;
-                    ++cc;
-                }
-                if ((unsigned)c != cab) { fresh = false; src = (int)cab; }
-            }
-            if (fresh) {
-                const int xi = ta.xidx[ab];
+            const int src = MuxCoef<R, P>::ab_source(c);
+            if (src == c) {
+                const int xi = mc.xi[c];
                 const R xc = xi >= 0 ? clip_unit<R>(ta.xrow[xi]) : (R)0;
                 cx[c] = xc;
                 sx[c] = qk_sqrt((R(1) - xc) * (R(1) + xc));
@@ -320,10 +360,8 @@ QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, A* acc) {
             QK_UNROLL
             for (int j = 0; j < NLOC; ++j) {
                 if (!((j >> kx) & 1)) {
-                    // compress j -> c
-                    int c = 0, cc = 0;
-                    for (int k = 0; k < T; ++k) if (k != kx && k != kw) { c |= ((j >> k) & 1) << cc; ++cc; }
-                    if (MODE == 0 || dloc[c] >= r + 1) rot(v[j], v[j | (1 << kx)], cx[c], sx[c]);
+                    const int c = MuxCoef<R, P>::compress(j);
+                    if (MODE == 0 || mc.dloc[c] >= r + 1) rot(v[j], v[j | (1 << kx)], cx[c], sx[c]);
                 }
             }
         }
@@ -331,9 +369,8 @@ QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, A* acc) {
         QK_UNROLL
         for (int j = 0; j < NLOC; ++j) {
             if (!((j >> kw) & 1)) {
-                int c = 0, cc = 0;
-                for (int k = 0; k < T; ++k) if (k != kx && k != kw) { c |= ((j >> k) & 1) << cc; ++cc; }
-                rot(v[j], v[j | (1 << kw)], cw[c], sw[c]);
+                const int c = MuxCoef<R, P>::compress(j);
+                rot(v[j], v[j | (1 << kw)], mc.cw[c], mc.sw[c]);
             }
         }
     }
@@ -357,7 +394,20 @@ QK_HD void run_stage(A* state, unsigned t, const TileArgs<R>& ta, A* acc) {
                 const unsigned dj = dep_local(p, S, j);
                 if ((dj & nonb) == 0) {
                     const unsigned b = (((unsigned)ta.b_hi << NBT) | ((base | dj) >> P::BIT_B0));
-                    add_amp(acc[b], v[j]);
+                    if constexpr (DIRECT) {
+                        if (ta.out_row != nullptr && (int)b < ta.K) {
+                            ta.out_row[b] = (double)v[j].re * ta.out_scale;
+                            if (ta.amp_row != nullptr) {
+                                Cplx<R> z;
+                                z.re = (R)((double)v[j].re * ta.amp_scale);
+                                if constexpr (A::is_complex) z.im = (R)((double)v[j].im * ta.amp_scale);
+                                else z.im = (R)0;
+                                reinterpret_cast<Cplx<R>*>(ta.amp_row)[b] = z;
+                            }
+                        }
+                    } else {
+                        add_amp(acc[b], v[j]);
+                    }
                 }
             }
         }

@@ -23,7 +23,8 @@ struct LaunchParams {
     int N, K, D, NA, NB;
     double out_scale;        // 1 / (N (D+1))
     double amp_scale;        // 2^-(m + 2l + n_a)/2
-    int tma_ok;              // x is 16-byte aligned and SPI*N*8 is a multiple of 16
+    int tma_ok;              // x is 16-byte aligned and a full tile is a multiple of 16 bytes
+    int sub;                 // sub-iterations per x tile (tile = SPI * sub samples)
 };
 
 // ------------------------------------------------------------------ PTX bits
@@ -68,19 +69,20 @@ template <int G, int NT> __device__ __forceinline__ void group_sync(int slot) {
     }
 }
 
-template <class A, typename R, class P, int MODE, int G, int NT, int S>
+template <class A, typename R, class P, int MODE, bool DIRECT, int G, int NT, int S>
 struct StageRunner {
-    static __device__ __forceinline__ void run(A* st, unsigned t, const TileArgs<R>& ta, A* acc, int slot) {
+    static __device__ __forceinline__ void run(A* st, unsigned t, const TileArgs<R>& ta, const MuxCoef<R, P>& mc,
+                                               A* acc, int slot) {
         constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
         if constexpr (S < p.ns) {
-            run_stage<A, R, P, S, MODE>(st, t, ta, acc);
+            run_stage<A, R, P, S, MODE, DIRECT>(st, t, ta, mc, acc);
             if constexpr (S + 1 < p.ns) group_sync<G, NT>(slot);
-            StageRunner<A, R, P, MODE, G, NT, S + 1>::run(st, t, ta, acc, slot);
+            StageRunner<A, R, P, MODE, DIRECT, G, NT, S + 1>::run(st, t, ta, mc, acc, slot);
         }
     }
 };
 
-template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP>
+template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP, bool FULL>
 struct KernelCfg {
     static constexpr int FW = sizeof(A) == 16 ? 3 : (sizeof(A) == 8 ? 4 : 5);
     using P = Plan<L, NAT, NBT, T, FW, PREP>;
@@ -88,37 +90,41 @@ struct KernelCfg {
     static constexpr int ST = 1 << QT;
     static constexpr int G = 1 << (QT - T);
     static_assert(G <= NT, "thread group larger than the CTA");
-    static constexpr int SPI = NT / G;
+    static constexpr int SPI = NT / G;                 // samples in flight per CTA
     static_assert(G <= 32 || G == NT || SPI <= 15, "not enough named barriers");
     static constexpr size_t state_bytes = (size_t)SPI * ST * sizeof(A);
 
-    static size_t xs_stride(int N) { return ((size_t)SPI * N + 1) & ~(size_t)1; }   // doubles, keeps 16-B alignment
-    static size_t smem_bytes(int N, int NB) {
-        size_t acc = (((size_t)SPI << NB) * sizeof(A) + 15) & ~(size_t)15;
-        return state_bytes + acc + 2 * xs_stride(N) * sizeof(double) + 2 * sizeof(unsigned long long);
+    // x tile = SPI * sub samples (sub sub-iterations between two CTA-wide barriers)
+    static size_t xs_stride(int N, int sub) { return ((size_t)SPI * sub * N + 1) & ~(size_t)1; }   // doubles, 16-B aligned
+    static __host__ __device__ size_t acc_bytes(int NB) { return (((size_t)SPI << NB) * sizeof(A) + 15) & ~(size_t)15; }
+    static size_t smem_bytes(int N, int NB, int sub) {
+        return state_bytes + acc_bytes(NB) + 2 * xs_stride(N, sub) * sizeof(double) + 2 * sizeof(unsigned long long);
     }
 };
 
-template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP>
+template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP, bool FULL>
 __global__ void __launch_bounds__(NT, MINB) qkan_forward_kernel(const LaunchParams p) {
-    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
+    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
     using P = typename C::P;
     constexpr int G = C::G, SPI = C::SPI, ST = C::ST;
+    constexpr P plan = make_plan<L, NAT, NBT, T, C::FW, PREP>();
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     A* state = reinterpret_cast<A*>(smem_raw);
     const int Kpad = 1 << p.NB;
-    const size_t acc_bytes = (((size_t)SPI << p.NB) * sizeof(A) + 15) & ~(size_t)15;
     A* accs = reinterpret_cast<A*>(smem_raw + C::state_bytes);
-    double* xs = reinterpret_cast<double*>(smem_raw + C::state_bytes + acc_bytes);
-    const size_t xstride = ((size_t)SPI * p.N + 1) & ~(size_t)1;
+    double* xs = reinterpret_cast<double*>(smem_raw + C::state_bytes + C::acc_bytes(p.NB));
+    const int sub = p.sub;
+    const int tile = SPI * sub;                              // samples per CTA iteration
+    const size_t xstride = ((size_t)tile * p.N + 1) & ~(size_t)1;
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(xs + 2 * xstride);
 
     const int tid = threadIdx.x;
     const int slot = tid / G;
     const unsigned t = tid % G;
-    const long long n_it = (p.B + SPI - 1) / SPI;
+    const long long n_it = (p.B + tile - 1) / tile;
     const int n_ahi = 1 << (p.NA - NAT), n_bhi = 1 << (p.NB - NBT);
+    const bool one_sector = (n_ahi == 1 && n_bhi == 1);
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -127,12 +133,16 @@ __global__ void __launch_bounds__(NT, MINB) qkan_forward_kernel(const LaunchPara
     }
     __syncthreads();
 
-    // stage the x rows of iteration `it` into buffer `b`
+    // stage the x rows of iteration `it` into buffer `b`: one 1-D TMA bulk copy when the tile
+    // is 16-byte granular, plain coalesced loads otherwise (ragged tail, odd N)
+    auto tile_bytes = [&](long long it) -> unsigned {
+        const long long s0 = it * tile;
+        const int ns = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
+        return (unsigned)ns * (unsigned)p.N * 8u;
+    };
     auto issue_x = [&](long long it, int b) {
-        const long long s0 = it * SPI;
-        const int ns = (int)((p.B - s0 < SPI) ? (p.B - s0) : SPI);
-        const unsigned bytes = (unsigned)ns * (unsigned)p.N * 8u;
-        const double* src = p.x + s0 * p.N;
+        const unsigned bytes = tile_bytes(it);
+        const double* src = p.x + it * tile * p.N;
         double* dst = xs + (size_t)b * xstride;
         if (p.tma_ok && (bytes & 15u) == 0) {
             if (tid == 0) {
@@ -141,13 +151,8 @@ __global__ void __launch_bounds__(NT, MINB) qkan_forward_kernel(const LaunchPara
                 tma_load_1d(dst, src, bytes, &mbar[b]);
             }
         } else {
-            for (int i = tid; i < ns * p.N; i += NT) dst[i] = src[i];
+            for (int i = tid; i < (int)(bytes >> 3); i += NT) dst[i] = src[i];
         }
-    };
-    auto x_is_tma = [&](long long it) {
-        const long long s0 = it * SPI;
-        const int ns = (int)((p.B - s0 < SPI) ? (p.B - s0) : SPI);
-        return p.tma_ok && (((unsigned)ns * (unsigned)p.N * 8u) & 15u) == 0;
     };
 
     long long it = blockIdx.x;
@@ -159,15 +164,31 @@ __global__ void __launch_bounds__(NT, MINB) qkan_forward_kernel(const LaunchPara
     A* st = state + (size_t)slot * ST;
     A* acc = accs + ((size_t)slot << p.NB);
 
+    TileArgs<R> ta;
+    ta.wtab = reinterpret_cast<const CS<R>*>(p.wtab);
+    ta.xidx = p.xidx;
+    ta.NA = p.NA;
+    ta.D = p.D;
+    ta.K = p.K;
+    ta.a_hi = 0;
+    ta.b_hi = 0;
+    ta.xrow = nullptr;
+    ta.out_row = nullptr;
+    ta.amp_row = nullptr;
+    ta.out_scale = p.out_scale;
+    ta.amp_scale = p.amp_scale;
+    MuxCoef<R, P> mc;
+    if (one_sector) load_mux_coefs<R, P>(mc, t, ta);     // weight rotations stay in registers for the whole launch
+
     for (; it < n_it; it += gridDim.x, buf ^= 1) {
         const long long nxt = it + gridDim.x;
         if (nxt < n_it) issue_x(nxt, buf ^ 1);
-        if (x_is_tma(it)) {
+        if (p.tma_ok && (tile_bytes(it) & 15u) == 0) {
             if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
         }
-        const long long s0 = it * SPI;
-        const int nsamp = (int)((p.B - s0 < SPI) ? (p.B - s0) : SPI);
+        const long long s0 = it * tile;
+        const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
         const double* xt = xs + (size_t)buf * xstride;
 
         // range check of the raw inputs (the reference prints a warning and clips)
@@ -178,49 +199,62 @@ __global__ void __launch_bounds__(NT, MINB) qkan_forward_kernel(const LaunchPara
         }
         if (bad) atomicAdd(p.oor, (unsigned long long)bad);
 
-        for (int b = (int)t; b < Kpad; b += G) set_amp(acc[b], 0.0);
-        group_sync<G, NT>(slot);
-
-        TileArgs<R> ta;
-        ta.wtab = reinterpret_cast<const CS<R>*>(p.wtab);
-        ta.xidx = p.xidx;
-        ta.xrow = xt + (size_t)(slot < nsamp ? slot : 0) * p.N;
-        ta.NA = p.NA;
-        ta.D = p.D;
-        constexpr P plan = make_plan<L, NAT, NBT, T, C::FW, PREP>();
-        for (int bh = 0; bh < n_bhi; ++bh) {
-            for (int ah = 0; ah < n_ahi; ++ah) {
-                if (sector_is_padding(ah, bh, NAT, NBT, p.N, p.K)) continue;
-                ta.a_hi = ah;
-                ta.b_hi = bh;
+        // sub-iterations: SPI samples at a time, only group-level synchronisation inside
+        const int nsub = (nsamp + SPI - 1) / SPI;
+        for (int si = 0; si < nsub; ++si) {
+            const int ls = si * SPI + slot;                   // sample within the tile
+            const bool valid = ls < nsamp;
+            ta.xrow = xt + (size_t)(valid ? ls : 0) * p.N;
+            if constexpr (FULL) {
+                // whole register on chip: read-out goes from registers to global memory
+                const long long o = (s0 + ls) * p.K;
+                ta.out_row = valid ? p.out + o : nullptr;
+                ta.amp_row = (valid && p.amps) ? (void*)(reinterpret_cast<Cplx<R>*>(p.amps) + o) : nullptr;
                 if constexpr (PREP == 0) {
-                    // |0...0> in shared memory; the initial Hadamards run as ordinary passes
                     for (int i = (int)t; i < ST; i += G) set_amp(st[i], i == 0 ? 1.0 : 0.0);
                     group_sync<G, NT>(slot);
                 }
-                StageRunner<A, R, P, MODE, G, NT, 0>::run(st, t, ta, acc, slot);
-                // the next sector's first store must not overtake this sector's last loads
+                StageRunner<A, R, P, MODE, true, G, NT, 0>::run(st, t, ta, mc, acc, slot);
+                // the next sample's first store must not overtake this sample's last loads
                 if constexpr (plan.ns > 1) group_sync<G, NT>(slot);
+                continue;
             }
-        }
-        if constexpr (plan.ns == 1) group_sync<G, NT>(slot);
-
-        if (slot < nsamp) {
-            for (int b = (int)t; b < p.K; b += G) {
-                const A a = acc[b];
-                const long long o = (s0 + slot) * p.K + b;
-                p.out[o] = (double)a.re * p.out_scale;
-                if (p.amps) {
-                    R im = 0;
-                    if constexpr (A::is_complex) im = a.im;
-                    Cplx<R> z;
-                    z.re = (R)((double)a.re * p.amp_scale);
-                    z.im = (R)((double)im * p.amp_scale);
-                    reinterpret_cast<Cplx<R>*>(p.amps)[o] = z;
+            for (int b = (int)t; b < Kpad; b += G) set_amp(acc[b], 0.0);
+            group_sync<G, NT>(slot);
+            for (int bh = 0; bh < n_bhi; ++bh) {
+                for (int ah = 0; ah < n_ahi; ++ah) {
+                    if (sector_is_padding(ah, bh, NAT, NBT, p.N, p.K)) continue;
+                    ta.a_hi = ah;
+                    ta.b_hi = bh;
+                    if constexpr (PREP == 0) {
+                        // |0...0> in shared memory; the initial Hadamards run as ordinary passes
+                        for (int i = (int)t; i < ST; i += G) set_amp(st[i], i == 0 ? 1.0 : 0.0);
+                        group_sync<G, NT>(slot);
+                    }
+                    load_mux_coefs<R, P>(mc, t, ta);
+                    StageRunner<A, R, P, MODE, false, G, NT, 0>::run(st, t, ta, mc, acc, slot);
+                    if constexpr (plan.ns > 1) group_sync<G, NT>(slot);
                 }
             }
+            if constexpr (plan.ns == 1) group_sync<G, NT>(slot);
+            if (valid) {
+                for (int b = (int)t; b < p.K; b += G) {
+                    const A a = acc[b];
+                    const long long o = (s0 + ls) * p.K + b;
+                    p.out[o] = (double)a.re * p.out_scale;
+                    if (p.amps) {
+                        R im = 0;
+                        if constexpr (A::is_complex) im = a.im;
+                        Cplx<R> z;
+                        z.re = (R)((double)a.re * p.amp_scale);
+                        z.im = (R)((double)im * p.amp_scale);
+                        reinterpret_cast<Cplx<R>*>(p.amps)[o] = z;
+                    }
+                }
+            }
+            group_sync<G, NT>(slot);      // acc is re-zeroed by the next sub-iteration
         }
-        __syncthreads();
+        __syncthreads();                  // everyone is done with xs[buf] before it is refilled
     }
 }
 
@@ -230,6 +264,8 @@ struct KernelInfo {
     int mode;     // 0 = compat, 1 = paper
     int prep;     // 1 = closed-form state preparation, 0 = initial Hadamards executed as gates
     int prio;     // selection priority among kernels that fit a shape
+    int variant;  // tuning variant id (env QKAN_VARIANT=<id> prefers it); 0 = default
+    int full;     // 1: only for shapes whose whole register is the tile (direct read-out, no sector loop)
     int L, NAT, NBT, T, NT;
     int stages;
     int spi;
@@ -237,23 +273,31 @@ struct KernelInfo {
     const void* func;
 };
 
-template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP>
+template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP, bool FULL>
 cudaError_t launch_forward(const LaunchParams& p, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
-    auto kern = qkan_forward_kernel<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
-    const size_t smem = C::smem_bytes(p.N, p.NB);
+    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
+    auto kern = qkan_forward_kernel<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
+    // x tile: about 4 KiB per buffer, but keep >= 4 tiles per resident CTA for load balance
+    int sub = (int)(4096 / ((size_t)C::SPI * p.N * 8));
+    if (sub > 32) sub = 32;
+    if (sub < 1) sub = 1;
+    size_t smem = C::smem_bytes(p.N, p.NB, sub);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const long long n_it = (p.B + C::SPI - 1) / C::SPI;
-    long long grid = (long long)sm_count * per_sm;
+    const long long resident = (long long)sm_count * per_sm;
+    while (sub > 1 && (p.B + (long long)C::SPI * sub - 1) / ((long long)C::SPI * sub) < 4 * resident) sub >>= 1;
+    smem = C::smem_bytes(p.N, p.NB, sub);
+    const long long n_it = (p.B + (long long)C::SPI * sub - 1) / ((long long)C::SPI * sub);
+    long long grid = resident;
     if (grid > n_it) grid = n_it;
     if (grid < 1) grid = 1;
     LaunchParams q = p;
-    q.tma_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0 && (((size_t)C::SPI * p.N * 8) & 15u) == 0) ? 1 : 0;
+    q.sub = sub;
+    q.tma_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0 && (((size_t)C::SPI * sub * p.N * 8) & 15u) == 0) ? 1 : 0;
     if (grid_out) *grid_out = (int)grid;
     if (smem_out) *smem_out = (int)smem;
     kern<<<(unsigned)grid, NT, smem, stream>>>(q);
@@ -265,20 +309,22 @@ template <> struct AmpId<Cplx<double>> { static constexpr int v = 0; };
 template <> struct AmpId<Cplx<float>> { static constexpr int v = 1; };
 template <> struct AmpId<Real<double>> { static constexpr int v = 2; };
 
-template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP>
+template <class A, typename R, int L, int NAT, int NBT, int T, int NT, int MINB, int MODE, int PREP, bool FULL>
 KernelInfo make_info() {
-    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
+    using C = KernelCfg<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
     constexpr auto plan = make_plan<L, NAT, NBT, T, C::FW, PREP>();
     KernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = MODE;
     k.prep = PREP;
     k.prio = 0;
+    k.variant = 0;
+    k.full = FULL ? 1 : 0;
     k.L = L; k.NAT = NAT; k.NBT = NBT; k.T = T; k.NT = NT;
     k.stages = plan.ns;
     k.spi = C::SPI;
-    k.launch = &launch_forward<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
-    k.func = (const void*)qkan_forward_kernel<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP>;
+    k.launch = &launch_forward<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
+    k.func = (const void*)qkan_forward_kernel<A, R, L, NAT, NBT, T, NT, MINB, MODE, PREP, FULL>;
     return k;
 }
 

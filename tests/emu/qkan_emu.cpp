@@ -4,19 +4,24 @@
 // by barriers on the GPU, so sequential in-place execution is equivalent.  Lets the CPU
 // test-suite check the compile-time plans, swizzle and read-out against the oracle.
 #include "../../qkan_implementation_b200/csrc/qkan_core.cuh"
+#include "../../qkan_implementation_b200/csrc/qkan_block.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdio>
 
 using namespace qkan;
 
-template <class A, typename R, class P, int MODE, int S>
+template <class A, typename R, class P, int MODE, bool DIRECT, int S>
 struct StageLoop {
     static void run(A* state, const TileArgs<R>& ta, A* acc) {
         constexpr P p = make_plan<P::L, P::NAT, P::NBT, P::T, P::FW, P::PREP>();
         if constexpr (S < p.ns) {
-            for (unsigned t = 0; t < (1u << P::NL); ++t) run_stage<A, R, P, S, MODE>(state, t, ta, acc);
-            StageLoop<A, R, P, MODE, S + 1>::run(state, ta, acc);
+            for (unsigned t = 0; t < (1u << P::NL); ++t) {
+                MuxCoef<R, P> mc;
+                load_mux_coefs<R, P>(mc, t, ta);
+                run_stage<A, R, P, S, MODE, DIRECT>(state, t, ta, mc, acc);
+            }
+            StageLoop<A, R, P, MODE, DIRECT, S + 1>::run(state, ta, acc);
         }
     }
 };
@@ -37,16 +42,27 @@ int emu_run(const double* x, const double* W, long long B, int N, int K, int D, 
     std::vector<A> acc(Kp);
     const int n_ahi = 1 << (NA - NAT), n_bhi = 1 << (NB - NBT);
     const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    bool direct = false;
     for (long long s = 0; s < B; ++s) {
         for (auto& a : acc) set_amp(a, 0.0);
         for (int bh = 0; bh < n_bhi; ++bh)
             for (int ah = 0; ah < n_ahi; ++ah) {
                 if (sector_is_padding(ah, bh, NAT, NBT, N, K)) continue;
-                TileArgs<R> ta{wtab.data(), xidx.data(), x + s * N, NA, ah, bh, D};
+                TileArgs<R> ta{wtab.data(), xidx.data(), x + s * N, NA, ah, bh, D, K, nullptr, nullptr,
+                               1.0 / ((double)N * (D + 1)), amp_scale};
                 if (PREP == 0) for (size_t i = 0; i < state.size(); ++i) set_amp(state[i], i == 0 ? 1.0 : 0.0);
-                StageLoop<A, R, P, MODE, 0>::run(state.data(), ta, acc.data());
+                if (NAT == NA && NBT == NB) {      // whole register in the tile: direct read-out path
+                    std::vector<Cplx<R>> arow(K);
+                    ta.out_row = out + s * K;
+                    ta.amp_row = amps ? arow.data() : nullptr;
+                    StageLoop<A, R, P, MODE, true, 0>::run(state.data(), ta, acc.data());
+                    if (amps) for (int b = 0; b < K; ++b) { amps[2 * (s * K + b)] = arow[b].re; amps[2 * (s * K + b) + 1] = arow[b].im; }
+                    direct = true;
+                } else {
+                    StageLoop<A, R, P, MODE, false, 0>::run(state.data(), ta, acc.data());
+                }
             }
-        for (int b = 0; b < K; ++b) {
+        if (!direct) for (int b = 0; b < K; ++b) {
             out[s * K + b] = (double)acc[b].re / ((double)N * (D + 1));
             if (amps) {
                 amps[2 * (s * K + b)] = (double)acc[b].re * amp_scale;
@@ -87,6 +103,86 @@ extern "C" int qkan_emu_forward(int cfg, const double* x, const double* W, long 
         CASE(19, Cplx, double, 4, 2, 2, 4, 0)   // N4 K4 D10
     }
     return -2;
+}
+
+// ---- block engine: lanes of a group run sequentially, the xor butterfly is replayed on arrays
+template <class A, typename R, int U, int MODE>
+int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, double* out, double* amps) {
+    const BlockLayout lay = plan_block_layout(N, K, D, min_g);
+    if (lay.U != U) return -3;
+    const int rowlen = N * (D + 1);
+    const long long E = (long long)K * rowlen;
+    std::vector<CS<R>> wtab(E);
+    std::vector<int> xitab(E);
+    for (long long e = 0; e < E; ++e) fill_block_entry<R>(e, W, N, K, D, wtab.data(), xitab.data());
+    const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2;
+    int NA = 0, NB = 0, L = 0;
+    while ((1 << NA) < N) ++NA;
+    while ((1 << NB) < K) ++NB;
+    while ((1 << L) < D + 1) ++L;
+    const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    for (long long s = 0; s < B; ++s) {
+        std::vector<CS<R>> cs(N);
+        for (int n = 0; n < N; ++n) { R c = clip_unit<R>(x[s * N + n]); cs[n].c = c; cs[n].s = qk_sqrt((R(1) - c) * (R(1) + c)); }
+        for (int bi = 0; bi < lay.brows; ++bi)
+            for (int k = 0; k < G_k; ++k) {
+                const int b = bi * G_k + k;
+                std::vector<A> acc(G_r);
+                for (int r = 0; r < G_r; ++r) {
+                    set_amp(acc[r], 0.0);
+                    for (int pi = 0; pi < lay.passes; ++pi) {
+                        R cx[U], sx[U], cw[U], sw[U];
+                        int deg[U];
+                        for (int u = 0; u < U; ++u) {
+                            const int i = (pi * U + u) * G_r + r;
+                            const bool live = b < K && i < rowlen;
+                            cw[u] = 0; sw[u] = 1; cx[u] = 0; sx[u] = 1; deg[u] = 0;
+                            if (live) {
+                                const long long e = (long long)b * rowlen + i;
+                                cw[u] = wtab[e].c; sw[u] = wtab[e].s;
+                                const int xi = xitab[e] & 0xFFFFF;
+                                deg[u] = xitab[e] >> 20;
+                                cx[u] = cs[xi].c; sx[u] = cs[xi].s;
+                            }
+                        }
+                        A part = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, D);
+                        add_amp(acc[r], part);
+                    }
+                }
+                for (int m = G_r >> 1; m >= 1; m >>= 1) {
+                    std::vector<A> nxt(acc);
+                    for (int r = 0; r < G_r; ++r) add_amp(nxt[r], acc[r ^ m]);
+                    acc = nxt;
+                }
+                if (b < K) {
+                    out[s * K + b] = (double)acc[0].re / ((double)N * (D + 1));
+                    if (amps) {
+                        amps[2 * (s * K + b)] = (double)acc[0].re * amp_scale;
+                        if constexpr (A::is_complex) amps[2 * (s * K + b) + 1] = (double)acc[0].im * amp_scale;
+                        else amps[2 * (s * K + b) + 1] = 0.0;
+                    }
+                }
+            }
+    }
+    return 0;
+}
+
+// amp: 0 c128, 1 c64, 2 r64
+extern "C" int qkan_emu_block_forward(int amp, int mode, int min_g, const double* x, const double* W, long long B, int N, int K,
+                                      int D, double* out, double* amps) {
+    const BlockLayout lay = plan_block_layout(N, K, D, min_g);
+#define BCASE(AMP, A, R, MODE, UU) \
+    if (amp == AMP && mode == MODE && lay.U == UU) return emu_block<A<R>, R, UU, MODE>(x, W, B, N, K, D, min_g, out, amps);
+    BCASE(0, Cplx, double, 0, 4) BCASE(0, Cplx, double, 0, 2) BCASE(0, Cplx, double, 0, 1)
+    BCASE(0, Cplx, double, 1, 4) BCASE(0, Cplx, double, 1, 2) BCASE(0, Cplx, double, 1, 1)
+    BCASE(1, Cplx, float, 0, 4) BCASE(1, Cplx, float, 0, 2) BCASE(1, Cplx, float, 0, 1)
+    BCASE(2, Real, double, 0, 4) BCASE(2, Real, double, 0, 2) BCASE(2, Real, double, 0, 1)
+    return -2;
+}
+extern "C" void qkan_emu_block_layout(int N, int K, int D, int min_g, int* out6, double* eff) {
+    const BlockLayout l = plan_block_layout(N, K, D, min_g);
+    out6[0] = l.U; out6[1] = l.g_r_log2; out6[2] = l.g_k_log2; out6[3] = l.passes; out6[4] = l.brows;
+    *eff = l.efficiency;
 }
 
 // plan dump for debugging / DESIGN.md

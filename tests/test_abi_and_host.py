@@ -39,7 +39,8 @@ def test_abi_argument_errors_without_gpu():
     assert lib.qkan_layer_create(ctypes.byref(h), 0, 4, 3, 0, 0, 1, 0) == b.ERR_BAD_SHAPE
     assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, -1, 0, 0, 1, 0) == b.ERR_BAD_SHAPE
     assert b"positive" in lib.qkan_last_error()
-    assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, 64, 0, 0, 1, 0) == b.ERR_UNSUPPORTED   # D > 31
+    assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, 64, 0, 0, 0, 0) == b.ERR_UNSUPPORTED   # staged engine: D <= 31
+    assert lib.qkan_layer_create(ctypes.byref(h), 4, 4, 4096, 0, 0, 1, 0) == b.ERR_UNSUPPORTED  # block engine: D < 2048
     assert lib.qkan_layer_forward(None, None, 1, None, None, None) == b.ERR_BAD_SHAPE
 
 

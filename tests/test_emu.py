@@ -37,3 +37,31 @@ def test_emulated_kernel_matches_oracle(emu, cfg, prep_gates):
     spec = o.circuit_spec(N, K, D)
     assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
     assert np.abs(amps[..., 1]).max() == 0.0
+
+
+BLOCK_SHAPES = [(4, 4, 3), (4, 8, 2), (8, 4, 2), (3, 2, 4), (8, 8, 5), (5, 3, 1), (16, 16, 8), (8, 8, 1), (8, 8, 16),
+                (4, 4, 10), (1, 1, 0), (2, 2, 1), (1, 5, 2), (7, 1, 3), (33, 3, 2), (100, 10, 5), (4, 4, 40), (784, 10, 5)]
+
+
+@pytest.mark.parametrize("min_g", [0, 3, 5])
+@pytest.mark.parametrize("N,K,D", BLOCK_SHAPES)
+def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
+    """qkan_block.cuh (layout planner, table entries, block evolution, xor-butterfly read-out) run lane by lane."""
+    import ctypes
+    f = emu.qkan_emu_block_forward
+    f.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    rng = np.random.default_rng(N * 31 + K * 7 + D + min_g)
+    B = 3
+    x = rng.uniform(-1.2, 1.2, (B, N))
+    x[1] = 0.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    spec = o.circuit_spec(N, K, D)
+    for amp, mode, tol in ((0, 0, 1e-14), (0, 1, 1e-14), (1, 0, 1e-5), (2, 0, 1e-14)):
+        out = np.zeros((B, K))
+        amps = np.zeros((B, K, 2))
+        rc = f(amp, mode, min_g, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data)
+        assert rc == 0
+        ref = o.forward_closed_form(x, W, N, K, D, "paper" if mode else "compat")
+        assert np.abs(out - ref).max() <= tol
+        assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
+        assert np.abs(amps[..., 1]).max() == 0.0

@@ -222,7 +222,8 @@ def test_c_abi_direct(Q):
     assert lib.qkan_layer_forward(h, x.data_ptr(), B, out.data_ptr(), None, None) == 0
     info = b.KernelInfo()
     assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
-    assert info.qubits == 8 and info.flops_alg == 21504 and info.grid > 0
+    assert info.qubits == 8 and info.flops_survey == 21504 and info.grid > 0
+    assert info.engine == 0 and info.blocks == 64 and info.flops_exec == 64 * (24 * 3 + 8)
     lib.qkan_layer_destroy(h)
     assert b.measure_fma_peak(0, True) > 5.0
 

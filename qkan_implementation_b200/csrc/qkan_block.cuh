@@ -147,14 +147,18 @@ template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) 
     return r;
 }
 
-template <class A, typename R, int U, int MODE, int NT, int MINB>
+// RESIDENT: every live block of the layer has its own (lane, u) slot (one pass, one row step), so
+// the weight rotations, x offsets and degrees stay in registers for the whole launch and the
+// per-sample body is straight-line code.  Otherwise the lane streams its blocks pass by pass.
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int G = 1 << (p.g_r_log2 + p.g_k_log2);
     const int G_r = 1 << p.g_r_log2;
+    const int G_k = 1 << p.g_k_log2;
     const int SPC = NT / G;                                  // samples in flight per CTA
     const int tile = SPC * p.sub;                            // samples per x tile
-    // smem: xs (TMA destination, raw x rows of the NEXT/current tile) | cs (clip + sqrt) | mbar
+    // smem: xs (TMA destination: raw x rows of the next tile) | cs (clip + sqrt of the current tile) | mbar
     const size_t xs_doubles = ((size_t)tile * p.N + 1) & ~(size_t)1;
     double* xs = reinterpret_cast<double*>(smem_raw);
     CS<R>* cs = reinterpret_cast<CS<R>*>(smem_raw + xs_doubles * sizeof(double));
@@ -165,9 +169,10 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int g = tid & (G - 1);
     const int r = g & (G_r - 1);
     const int k = g >> p.g_r_log2;
-    const int slot = tid / G;                                // sample slot inside the CTA
+    const int slot = tid >> (p.g_r_log2 + p.g_k_log2);       // sample slot inside the CTA
     const long long n_it = (p.B + tile - 1) / tile;
-    const CS<R>* wtab = reinterpret_cast<const CS<R>*>(p.wtab);
+    const CS<R>* __restrict__ wtab = reinterpret_cast<const CS<R>*>(p.wtab);
+    const int* __restrict__ xitab = p.xitab;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -194,34 +199,37 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         }
     };
 
-    // block coefficients that do not depend on the sample; kept in registers for the whole
-    // launch when every block of the layer is resident (one pass, one row per lane)
+    // sample-independent block coefficients of this lane: one load per launch when RESIDENT
     R cw[U], sw[U];
     int xi[U], deg[U];
     bool live[U];
-    auto load_items = [&](int bi, int pi) {
-        const int b = bi * (1 << p.g_k_log2) + k;
+    auto load_items = [&](int b, int i0) {
         QK_UNROLL
         for (int u = 0; u < U; ++u) {
-            const int i = (pi * U + u) * G_r + r;
+            const int i = i0 + u * G_r;
             live[u] = (b < p.K) && (i < p.rowlen);
-            const long long e = (long long)b * p.rowlen + i;
             CS<R> w;
             w.c = R(0); w.s = R(1);
             int packed = 0;
-            if (live[u]) { w = wtab[e]; packed = p.xitab[e]; }
+            if (live[u]) {
+                const long long e = (long long)b * p.rowlen + i;
+                w = wtab[e];
+                packed = xitab[e];
+            }
             cw[u] = w.c; sw[u] = w.s;
             xi[u] = packed & 0xFFFFF;
             deg[u] = packed >> 20;
         }
     };
-    const bool resident = (p.passes == 1 && p.brows == 1);
-    if (resident) load_items(0, 0);
+    if constexpr (RESIDENT) load_items(k, r);
 
     long long it = blockIdx.x;
     unsigned phase = 0;
     if (it < n_it) issue_x(it);
     __syncthreads();
+
+    const size_t row_stride = (size_t)SPC * p.N;             // cs entries between consecutive sub-iterations
+    const long long out_stride = (long long)SPC * p.K;
 
     for (; it < n_it; it += gridDim.x) {
         if (p.tma_ok && (tile_bytes(it) & 15u) == 0) { mbar_wait(&mbar[0], phase); phase ^= 1; }
@@ -247,39 +255,63 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         if (nxt < n_it) issue_x(nxt);                         // overlaps with the compute below
 
         const int nsub = (nsamp + SPC - 1) / SPC;
-        for (int si = 0; si < nsub; ++si) {
-            const int ls = si * SPC + slot;
+        const CS<R>* csrow = cs + (size_t)slot * p.N;
+        long long o = (s0 + slot) * p.K;
+        int ls = slot;
+        for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, ls += SPC) {
             const bool valid = ls < nsamp;
-            const CS<R>* csrow = cs + (size_t)(valid ? ls : 0) * p.N;
-            for (int bi = 0; bi < p.brows; ++bi) {
-                A acc;
-                set_amp(acc, 0.0);
-                for (int pi = 0; pi < p.passes; ++pi) {
-                    if (!resident) load_items(bi, pi);
-                    R cx[U], sx[U];
-                    QK_UNROLL
-                    for (int u = 0; u < U; ++u) {
-                        CS<R> e;
-                        e.c = R(0); e.s = R(1);
-                        if (live[u]) e = csrow[xi[u]];
-                        cx[u] = e.c; sx[u] = e.s;
-                    }
-                    const A part = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, p.D);
-                    add_amp(acc, part);
+            const CS<R>* row = valid ? csrow : cs;            // idle slots of a ragged tile read row 0
+            if constexpr (RESIDENT) {
+                R cx[U], sx[U];
+                QK_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    CS<R> e;
+                    e.c = R(0); e.s = R(1);
+                    if (live[u]) e = row[xi[u]];
+                    cx[u] = e.c; sx[u] = e.s;
                 }
+                A acc = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, p.D);
                 // UNPREPARE (H on deg) + SUM (H on a) + post-selection deg = a = 0: the sum over the
                 // row's blocks, finished across the G_r lanes with an xor butterfly
                 for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
-                const int b = bi * (1 << p.g_k_log2) + k;
-                if (valid && r == 0 && b < p.K) {
-                    const long long o = (s0 + ls) * p.K + b;
-                    p.out[o] = (double)acc.re * p.out_scale;
+                if (valid && r == 0 && k < p.K) {
+                    p.out[o + k] = (double)acc.re * p.out_scale;
                     if (p.amps) {
                         Cplx<R> z;
                         z.re = (R)((double)acc.re * p.amp_scale);
                         if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
                         else z.im = R(0);
-                        reinterpret_cast<Cplx<R>*>(p.amps)[o] = z;
+                        reinterpret_cast<Cplx<R>*>(p.amps)[o + k] = z;
+                    }
+                }
+            } else {
+                for (int b = k; b < p.brows * G_k; b += G_k) {
+                    A acc;
+                    set_amp(acc, 0.0);
+                    int i0 = r;
+                    for (int pi = 0; pi < p.passes; ++pi, i0 += U * G_r) {
+                        load_items(b, i0);
+                        R cx[U], sx[U];
+                        QK_UNROLL
+                        for (int u = 0; u < U; ++u) {
+                            CS<R> e;
+                            e.c = R(0); e.s = R(1);
+                            if (live[u]) e = row[xi[u]];
+                            cx[u] = e.c; sx[u] = e.s;
+                        }
+                        const A part = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, p.D);
+                        add_amp(acc, part);
+                    }
+                    for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
+                    if (valid && r == 0 && b < p.K) {
+                        p.out[o + b] = (double)acc.re * p.out_scale;
+                        if (p.amps) {
+                            Cplx<R> z;
+                            z.re = (R)((double)acc.re * p.amp_scale);
+                            if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
+                            else z.im = R(0);
+                            reinterpret_cast<Cplx<R>*>(p.amps)[o + b] = z;
+                        }
                     }
                 }
             }
@@ -308,9 +340,9 @@ struct BlockKernelInfo {
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
 
-template <class A, typename R, int U, int MODE, int NT, int MINB>
-cudaError_t launch_block(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB>;
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT>
+cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, RESIDENT>;
     BlockParams p = p0;
     const int SPC = NT / G;
     auto smem_for = [&](int sub) {
@@ -341,6 +373,13 @@ cudaError_t launch_block(const BlockParams& p0, int G, int sm_count, cudaStream_
     kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
     return cudaGetLastError();
 }
+template <class A, typename R, int U, int MODE, int NT, int MINB>
+cudaError_t launch_block(const BlockParams& p, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p.passes == 1 && p.brows == 1)
+        return launch_block_impl<A, R, U, MODE, NT, MINB, true>(p, G, sm_count, stream, grid_out, smem_out);
+    return launch_block_impl<A, R, U, MODE, NT, MINB, false>(p, G, sm_count, stream, grid_out, smem_out);
+}
+
 template <class A> struct AmpId;
 
 template <class A, typename R, int U, int MODE, int NT, int MINB>

@@ -67,74 +67,130 @@ inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, in
     return best;
 }
 
+// one live (or padding) block as the kernel reads it: the SELECT rotation, the byte offset of the
+// CHEB rotation pair inside the sample's cs row, and the term degree (paper mode)
+template <typename R> struct alignas(16) BlockRec {
+    R c, s;
+    int xoff;
+    int deg;
+};
+
 struct BlockParams {
     const double* x;            // [B, N]
-    const void* wtab;           // CS<R>[K * rowlen]: (w, sqrt(1-w^2)) of block e = b*rowlen + a*(D+1) + d
-    const int* xitab;           // int[K * rowlen]: x index (a + N b) / K  |  d << 20
+    const void* rec;            // BlockRec<R>[rows_pad][cols_pad], lane order (see fill_block_rec)
     double* out;                // [B, K]
     void* amps;                 // optional [B, K] complex
     unsigned long long* oor;
     long long B;
     int N, K, D;
-    int rowlen;                 // N * (D + 1) blocks per output row
+    int cols_pad;               // passes * G_r * U block slots per output row
     int g_r_log2, g_k_log2;     // lanes per row / rows in parallel inside a group
-    int passes;                 // ceil(rowlen / (G_r * U))
+    int passes;                 // ceil(N (D+1) / (G_r * U))
     int brows;                  // ceil(K / G_k)
     int sub;                    // sub-iterations per x tile
     int tma_ok;
     double out_scale, amp_scale;
+    double init[8];             // prepared block state, 4 complex amplitudes (re, im): (1,0,0,0) un-normalised
 };
 
-// one block entry of the tables (host or device)
+// Table slot (b, i) of the padded [brows * G_k][passes * G_r * U] grid.  Lane r of a row handles,
+// in pass pi, the U consecutive slots i = (pi * G_r + r) * U + u, so its loads are contiguous and
+// the row is read coalesced.  Slot i < N (D+1) is the block (a, d) = (i / (D+1), i % (D+1)) of row b:
+// weight W[d][a + N b] (column-major SUM reshape, QKANLayer.py:132; MulStep.py:69) and input
+// x[(a + N b) / K] (np.repeat dilation, ChebyshevStep.py:64).  Padding slots rotate by theta = pi
+// (c = 0) and read the row's dummy entry, so they add exactly 0 to the read-out.
 template <typename R>
-QK_HD void fill_block_entry(long long e, const double* W, int N, int K, int D, CS<R>* wtab, int* xitab) {
+QK_HD void fill_block_rec(long long slot, const double* W, int N, int K, int D, int cols_pad, BlockRec<R>* rec) {
     const int rowlen = N * (D + 1);
-    const int b = (int)(e / rowlen);
-    const int i = (int)(e - (long long)b * rowlen);
-    const int a = i / (D + 1), d = i - a * (D + 1);
-    const int flat = a + N * b;                         // QKANLayer.py:132 (column-major reshape)
-    const R w = (R)W[(long long)d * N * K + flat];      // MulStep.py:69
-    CS<R> cs;
-    cs.c = w;
-    cs.s = qk_sqrt((R(1) - w) * (R(1) + w));
-    wtab[e] = cs;
-    xitab[e] = (flat / K) | (d << 20);                  // ChebyshevStep.py:64 (np.repeat -> i // K)
+    const int b = (int)(slot / cols_pad);
+    const int i = (int)(slot - (long long)b * cols_pad);
+    BlockRec<R> q;
+    q.c = R(0); q.s = R(1);
+    q.xoff = N * (int)sizeof(CS<R>);                    // dummy (0, 1) entry at the end of every cs row
+    q.deg = 0;
+    if (b < K && i < rowlen) {
+        const int a = i / (D + 1), d = i - a * (D + 1);
+        const int flat = a + N * b;
+        const R w = (R)W[(long long)d * N * K + flat];
+        q.c = w;
+        q.s = qk_sqrt((R(1) - w) * (R(1) + w));
+        q.xoff = (flat / K) * (int)sizeof(CS<R>);
+        q.deg = d;
+    }
+    rec[slot] = q;
 }
 
-// evolve U blocks and return the sum of their (0,0) amplitudes.  v[u][fx + 2 fw].
-template <class A, typename R, int U, int MODE>
-QK_HD A evolve_blocks(const R (&cx)[U], const R (&sx)[U], const R (&cw)[U], const R (&sw)[U], const int (&deg)[U], int D) {
+// first output of a rotation pass only: u' = c u - s v (the f = 0 member of the pair)
+template <typename R> QK_HD Cplx<R> rot_lo(const Cplx<R>& u, const Cplx<R>& v, R c, R s) {
+    Cplx<R> o;
+    o.re = qk_fma(c, u.re, -(s * v.re));
+    o.im = qk_fma(c, u.im, -(s * v.im));
+    return o;
+}
+template <typename R> QK_HD Real<R> rot_lo(const Real<R>& u, const Real<R>& v, R c, R s) {
+    Real<R> o;
+    o.re = qk_fma(c, u.re, -(s * v.re));
+    return o;
+}
+
+// Evolve U blocks from the prepared state `init` (amplitudes v[fx + 2 fw]; a run-time value: the
+// kernel makes no use of it being (1, 0, 0, 0), real, or half zero) and return the sum of their
+// post-selected (f_x, f_w) = (0, 0) amplitudes.
+//   CHEB  applications 1 .. D-1: full rotation passes on both f_w halves       16 instr / 24 flops
+//   CHEB  application D and MUL: pruned to the backward light cone of the post-selected
+//         amplitude - (0,0) after MUL needs only the f_x = 0 outputs of the last CHEB pass
+//                                                                             8 + 4 instr / 12 + 6 flops
+//   read-out: one complex add per block                                        2 instr / 2 flops
+// (complex amplitudes; half of that for the real-only representation).
+// DT > 0: D is the compile-time constant DT (fully unrolled); DT = 0: run-time D.
+template <class A, typename R, int U, int MODE, int DT = 0>
+QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], const R (&cw)[U], const R (&sw)[U],
+                      const int (&deg)[U], int D) {
+    const int Dv = DT > 0 ? DT : D;
     A v[U][4];
     QK_UNROLL
     for (int u = 0; u < U; ++u) {
-        set_amp(v[u][0], 1.0);          // PREPARE'd, un-normalised
-        set_amp(v[u][1], 0.0);
-        set_amp(v[u][2], 0.0);
-        set_amp(v[u][3], 0.0);
+        QK_UNROLL
+        for (int q = 0; q < 4; ++q) v[u][q] = init[q];
     }
-    // CHEB: D applications of the input block-encoding, U and Z U^dagger Z alternating; as real
+    // CHEB: the input block-encoding applied D times, U and Z U^dagger Z alternating; as real
     // matrices both equal Ry(theta_x), so each application is the same rotation pass
-    for (int r = 0; r < D; ++r) {
+    auto coef = [&](int u, int r, R& c, R& s) {
+        c = cx[u]; s = sx[u];
+        if constexpr (MODE == 1) {                      // paper: term d gets d applications
+            const bool on = deg[u] >= r + 1;
+            c = on ? c : R(1);
+            s = on ? s : R(0);
+        }
+    };
+    auto cheb = [&](int r) {
         QK_UNROLL
         for (int u = 0; u < U; ++u) {
-            R c = cx[u], s = sx[u];
-            if constexpr (MODE == 1) {                  // paper: term d gets d applications
-                const bool on = deg[u] >= r + 1;
-                c = on ? c : R(1);
-                s = on ? s : R(0);
-            }
+            R c, s;
+            coef(u, r, c, s);
             rot(v[u][0], v[u][1], c, s);
             rot(v[u][2], v[u][3], c, s);
         }
+    };
+    if constexpr (DT > 0) {
+        QK_UNROLL
+        for (int r = 0; r + 1 < DT; ++r) cheb(r);
+    } else {
+        for (int r = 0; r + 1 < Dv; ++r) cheb(r);
     }
-    // MUL / SELECT on f_w, then read-out of (f_x, f_w) = (0, 0)
     A acc;
-    set_amp(acc, 0.0);
     QK_UNROLL
     for (int u = 0; u < U; ++u) {
-        rot(v[u][0], v[u][2], cw[u], sw[u]);
-        rot(v[u][1], v[u][3], cw[u], sw[u]);
-        add_amp(acc, v[u][0]);
+        A lo0 = v[u][0], lo2 = v[u][2];
+        if (Dv > 0) {                                   // last CHEB application, f_x = 0 outputs only
+            R c, s;
+            coef(u, Dv - 1, c, s);
+            lo0 = rot_lo(v[u][0], v[u][1], c, s);
+            lo2 = rot_lo(v[u][2], v[u][3], c, s);
+        }
+        const A z = rot_lo(lo0, lo2, cw[u], sw[u]);     // MUL / SELECT on f_w, (0,0) output
+        if (u == 0) acc = z;
+        else add_amp(acc, z);
     }
     return acc;
 }
@@ -147,10 +203,10 @@ template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) 
     return r;
 }
 
-// RESIDENT: every live block of the layer has its own (lane, u) slot (one pass, one row step), so
-// the weight rotations, x offsets and degrees stay in registers for the whole launch and the
-// per-sample body is straight-line code.  Otherwise the lane streams its blocks pass by pass.
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT>
+// RESIDENT: every block slot of the layer has its own (lane, u) (one pass, one row step), so the
+// records stay in registers for the whole launch and the per-sample body is straight-line code.
+// Otherwise the lane streams its records pass by pass (coalesced, L1/L2 resident).
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT, int DT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int G = 1 << (p.g_r_log2 + p.g_k_log2);
@@ -158,12 +214,13 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int G_k = 1 << p.g_k_log2;
     const int SPC = NT / G;                                  // samples in flight per CTA
     const int tile = SPC * p.sub;                            // samples per x tile
-    // smem: xs (TMA destination: raw x rows of the next tile) | cs (clip + sqrt of the current tile) | mbar
+    const int NP = p.N + 1;                                  // cs row: N rotation pairs + the dummy (0, 1)
+    // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (clip + sqrt of the current tile) | mbar[2]
     const size_t xs_doubles = ((size_t)tile * p.N + 1) & ~(size_t)1;
-    double* xs = reinterpret_cast<double*>(smem_raw);
-    CS<R>* cs = reinterpret_cast<CS<R>*>(smem_raw + xs_doubles * sizeof(double));
+    double* xs0 = reinterpret_cast<double*>(smem_raw);
+    CS<R>* cs = reinterpret_cast<CS<R>*>(smem_raw + 2 * xs_doubles * sizeof(double));
     unsigned long long* mbar =
-        reinterpret_cast<unsigned long long*>(smem_raw + xs_doubles * sizeof(double) + (((size_t)tile * p.N * sizeof(CS<R>) + 15) & ~(size_t)15));
+        reinterpret_cast<unsigned long long*>(smem_raw + 2 * xs_doubles * sizeof(double) + (((size_t)tile * NP * sizeof(CS<R>) + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x;
     const int g = tid & (G - 1);
@@ -171,12 +228,18 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int k = g >> p.g_r_log2;
     const int slot = tid >> (p.g_r_log2 + p.g_k_log2);       // sample slot inside the CTA
     const long long n_it = (p.B + tile - 1) / tile;
-    const CS<R>* __restrict__ wtab = reinterpret_cast<const CS<R>*>(p.wtab);
-    const int* __restrict__ xitab = p.xitab;
+    const BlockRec<R>* __restrict__ rec = reinterpret_cast<const BlockRec<R>*>(p.rec);
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
         fence_barrier_init();
+    }
+    // the dummy entries never change
+    for (int i = tid; i < tile; i += NT) {
+        CS<R> e;
+        e.c = R(0); e.s = R(1);
+        cs[(size_t)i * NP + p.N] = e;
     }
     __syncthreads();
 
@@ -185,54 +248,58 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         const int ns = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
         return (unsigned)ns * (unsigned)p.N * 8u;
     };
-    auto issue_x = [&](long long it) {
+    // stage the x rows of tile `it` into buffer b: one 1-D TMA bulk copy when the tile is 16-byte
+    // granular, plain coalesced loads otherwise (ragged tail, odd N)
+    auto issue_x = [&](long long it, int b) {
         const unsigned bytes = tile_bytes(it);
         const double* src = p.x + it * tile * p.N;
+        double* dst = xs0 + (size_t)b * xs_doubles;
         if (p.tma_ok && (bytes & 15u) == 0) {
             if (tid == 0) {
                 fence_proxy_async();
-                mbar_expect_tx(&mbar[0], bytes);
-                tma_load_1d(xs, src, bytes, &mbar[0]);
+                mbar_expect_tx(&mbar[b], bytes);
+                tma_load_1d(dst, src, bytes, &mbar[b]);
             }
         } else {
-            for (int i = tid; i < (int)(bytes >> 3); i += NT) xs[i] = src[i];
+            for (int i = tid; i < (int)(bytes >> 3); i += NT) dst[i] = src[i];
         }
     };
 
-    // sample-independent block coefficients of this lane: one load per launch when RESIDENT
+    A init[4];
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        init[q].re = (R)p.init[2 * q];
+        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
+    }
     R cw[U], sw[U];
-    int xi[U], deg[U];
-    bool live[U];
-    auto load_items = [&](int b, int i0) {
+    int xoff[U], deg[U];
+    auto load_recs = [&](const BlockRec<R>* rp) {
         QK_UNROLL
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * G_r;
-            live[u] = (b < p.K) && (i < p.rowlen);
-            CS<R> w;
-            w.c = R(0); w.s = R(1);
-            int packed = 0;
-            if (live[u]) {
-                const long long e = (long long)b * p.rowlen + i;
-                w = wtab[e];
-                packed = xitab[e];
-            }
-            cw[u] = w.c; sw[u] = w.s;
-            xi[u] = packed & 0xFFFFF;
-            deg[u] = packed >> 20;
+            const BlockRec<R> q = rp[u];
+            cw[u] = q.c; sw[u] = q.s; xoff[u] = q.xoff; deg[u] = q.deg;
         }
     };
-    if constexpr (RESIDENT) load_items(k, r);
+    if constexpr (RESIDENT) load_recs(rec + (size_t)k * p.cols_pad + (size_t)r * U);
 
+    // two tiles in flight: tile i is consumed while tiles i+1 and (after its pre-pass) i+2 are loading
     long long it = blockIdx.x;
-    unsigned phase = 0;
-    if (it < n_it) issue_x(it);
+    unsigned phase0 = 0, phase1 = 0;
+    int buf = 0;
+    if (it < n_it) issue_x(it, 0);
+    if (it + gridDim.x < n_it) issue_x(it + gridDim.x, 1);
     __syncthreads();
 
-    const size_t row_stride = (size_t)SPC * p.N;             // cs entries between consecutive sub-iterations
+    const size_t row_stride = (size_t)SPC * NP * sizeof(CS<R>);   // bytes between consecutive sub-iterations
     const long long out_stride = (long long)SPC * p.K;
+    const size_t pass_stride = (size_t)G_r * U;                   // records per pass
 
-    for (; it < n_it; it += gridDim.x) {
-        if (p.tma_ok && (tile_bytes(it) & 15u) == 0) { mbar_wait(&mbar[0], phase); phase ^= 1; }
+    for (; it < n_it; it += gridDim.x, buf ^= 1) {
+        if (p.tma_ok && (tile_bytes(it) & 15u) == 0) {
+            if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+            else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+        }
+        const double* xs = xs0 + (size_t)buf * xs_doubles;
         const long long s0 = it * tile;
         const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
 
@@ -247,30 +314,29 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
             CS<R> e;
             e.c = c;
             e.s = qk_sqrt((R(1) - c) * (R(1) + c));
-            cs[i] = e;
+            const int row = i / p.N;
+            cs[i + row] = e;                                  // row stride N + 1
         }
         if (bad) atomicAdd(p.oor, (unsigned long long)bad);
-        __syncthreads();                                      // cs complete, xs free again
-        const long long nxt = it + gridDim.x;
-        if (nxt < n_it) issue_x(nxt);                         // overlaps with the compute below
+        __syncthreads();                                      // cs complete, xs[buf] free again
+        const long long nxt = it + 2 * (long long)gridDim.x;
+        if (nxt < n_it) issue_x(nxt, buf);                    // overlaps with the compute of this and the next tile
 
         const int nsub = (nsamp + SPC - 1) / SPC;
-        const CS<R>* csrow = cs + (size_t)slot * p.N;
+        const char* csrow = reinterpret_cast<const char*>(cs) + (size_t)slot * NP * sizeof(CS<R>);
         long long o = (s0 + slot) * p.K;
         int ls = slot;
         for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, ls += SPC) {
             const bool valid = ls < nsamp;
-            const CS<R>* row = valid ? csrow : cs;            // idle slots of a ragged tile read row 0
+            const char* row = valid ? csrow : reinterpret_cast<const char*>(cs);   // idle slots of a ragged tile read row 0
             if constexpr (RESIDENT) {
                 R cx[U], sx[U];
                 QK_UNROLL
                 for (int u = 0; u < U; ++u) {
-                    CS<R> e;
-                    e.c = R(0); e.s = R(1);
-                    if (live[u]) e = row[xi[u]];
+                    const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
                     cx[u] = e.c; sx[u] = e.s;
                 }
-                A acc = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, p.D);
+                A acc = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
                 // UNPREPARE (H on deg) + SUM (H on a) + post-selection deg = a = 0: the sum over the
                 // row's blocks, finished across the G_r lanes with an xor butterfly
                 for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
@@ -285,21 +351,20 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     }
                 }
             } else {
-                for (int b = k; b < p.brows * G_k; b += G_k) {
+                const BlockRec<R>* rowp = rec + (size_t)k * p.cols_pad + (size_t)r * U;
+                for (int b = k; b < p.brows * G_k; b += G_k, rowp += (size_t)G_k * p.cols_pad) {
+                    const BlockRec<R>* rp = rowp;
                     A acc;
                     set_amp(acc, 0.0);
-                    int i0 = r;
-                    for (int pi = 0; pi < p.passes; ++pi, i0 += U * G_r) {
-                        load_items(b, i0);
+                    for (int pi = 0; pi < p.passes; ++pi, rp += pass_stride) {
+                        load_recs(rp);
                         R cx[U], sx[U];
                         QK_UNROLL
                         for (int u = 0; u < U; ++u) {
-                            CS<R> e;
-                            e.c = R(0); e.s = R(1);
-                            if (live[u]) e = row[xi[u]];
+                            const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
                             cx[u] = e.c; sx[u] = e.s;
                         }
-                        const A part = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, p.D);
+                        const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
                         add_amp(acc, part);
                     }
                     for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
@@ -321,34 +386,35 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 }
 
 template <typename R>
-__global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, CS<R>* wtab, int* xitab,
-                                                 unsigned long long* bad_weights) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long E = (long long)N * K * (D + 1);
-    if (e >= E) return;
-    fill_block_entry<R>(e, W, N, K, D, wtab, xitab);
-    const int rowlen = N * (D + 1);
-    const int b = (int)(e / rowlen), i = (int)(e % rowlen);
-    const int a = i / (D + 1), d = i % (D + 1);
-    const double w = W[(long long)d * N * K + a + N * b];
-    if (!(fabs(w) <= 1.0)) atomicAdd(bad_weights, 1ull);     // MulStep.py:36-37
+__global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int cols_pad, long long slots,
+                                                 BlockRec<R>* rec, unsigned long long* bad_weights) {
+    const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= slots) return;
+    fill_block_rec<R>(slot, W, N, K, D, cols_pad, rec);
+    const int b = (int)(slot / cols_pad), i = (int)(slot % cols_pad);
+    if (b < K && i < N * (D + 1)) {
+        const int a = i / (D + 1), d = i % (D + 1);
+        const double w = W[(long long)d * N * K + a + N * b];
+        if (!(fabs(w) <= 1.0)) atomicAdd(bad_weights, 1ull);     // MulStep.py:36-37
+    }
 }
 
 struct BlockKernelInfo {
     int amp, mode, U, NT, MINB;
+    int DT;                     // 0 = any D (run-time loop), else only for D == DT
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
 
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT>
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT, int DT>
 cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, RESIDENT>;
+    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, RESIDENT, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
     auto smem_for = [&](int sub) {
         const size_t tile = (size_t)SPC * sub;
-        const size_t xs = ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
-        const size_t cs = (tile * p.N * sizeof(CS<R>) + 15) & ~(size_t)15;
+        const size_t xs = 2 * ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
+        const size_t cs = (tile * (p.N + 1) * sizeof(CS<R>) + 15) & ~(size_t)15;
         return xs + cs + 16;
     };
     int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile
@@ -373,21 +439,22 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
     return cudaGetLastError();
 }
-template <class A, typename R, int U, int MODE, int NT, int MINB>
+template <class A, typename R, int U, int MODE, int NT, int MINB, int DT>
 cudaError_t launch_block(const BlockParams& p, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (DT > 0 && p.D != DT) return cudaErrorInvalidValue;
     if (p.passes == 1 && p.brows == 1)
-        return launch_block_impl<A, R, U, MODE, NT, MINB, true>(p, G, sm_count, stream, grid_out, smem_out);
-    return launch_block_impl<A, R, U, MODE, NT, MINB, false>(p, G, sm_count, stream, grid_out, smem_out);
+        return launch_block_impl<A, R, U, MODE, NT, MINB, true, DT>(p, G, sm_count, stream, grid_out, smem_out);
+    return launch_block_impl<A, R, U, MODE, NT, MINB, false, DT>(p, G, sm_count, stream, grid_out, smem_out);
 }
 
 template <class A> struct AmpId;
 
-template <class A, typename R, int U, int MODE, int NT, int MINB>
+template <class A, typename R, int U, int MODE, int NT, int MINB, int DT>
 BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
-    k.mode = MODE; k.U = U; k.NT = NT; k.MINB = MINB; k.is_default = is_default;
-    k.launch = &launch_block<A, R, U, MODE, NT, MINB>;
+    k.mode = MODE; k.U = U; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
+    k.launch = &launch_block<A, R, U, MODE, NT, MINB, DT>;
     return k;
 }
 #endif  // __CUDACC__

@@ -98,7 +98,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB" (0 = any)
         int fU = 0, fNT = 0, fMINB = 0;
         if (tune) sscanf(tune, "%d:%d:%d", &fU, &fNT, &fMINB);
-        const size_t per_x = 8 + 2 * amp_real_size(dtype);
+        const size_t per_x = 16 + 2 * amp_real_size(dtype);      // two raw x buffers + the (cos, sin) pair
         const int NTs[4] = {256, 128, 64, 32};
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
             const int NT = NTs[ni];
@@ -107,14 +107,16 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 const BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
                 const int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                 if (G < (1 << min_g) || G > NT) continue;
-                if ((size_t)(NT / G) * N * per_x > 72 * 1024) continue;
+                if ((size_t)(NT / G) * (N + 1) * per_x > 72 * 1024) continue;
+                const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
                     if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
                     if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
-                    bbest = &k;
-                    lay = cand;
-                    break;
+                    if (k.DT == max_degree && !getenv("QKAN_BLOCK_NO_DT")) { bbest = &k; break; }   // degree-specialised
+                    if (k.DT == 0 && !generic) generic = &k;
                 }
+                if (!bbest) bbest = generic;
+                if (bbest) lay = cand;
             }
         }
         if (!bbest) {
@@ -156,9 +158,10 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     l->sm_count = prop.multiProcessorCount;
     const size_t nab = (size_t)1 << (NA + NB);
     const size_t nblk = (size_t)N * K * (max_degree + 1);
+    (void)nblk;
     if (l->engine == 0) {
-        e = cudaMalloc(&l->wtab, nblk * 2 * amp_real_size(dtype));
-        if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nblk * sizeof(int));
+        const size_t slots = (size_t)l->lay.brows * (1u << l->lay.g_k_log2) * l->lay.passes * (1u << l->lay.g_r_log2) * l->lay.U;
+        e = cudaMalloc(&l->wtab, slots * (dtype == QKAN_COMPLEX64 ? sizeof(BlockRec<float>) : sizeof(BlockRec<double>)));
     } else {
         e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
         if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nab * sizeof(int));
@@ -197,14 +200,15 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
     const double* Wd = l->W_dev;
     CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
     if (l->engine == 0) {
-        const long long E = (long long)l->N * l->K * (l->D + 1);
-        const unsigned nt = 128, nb = (unsigned)((E + nt - 1) / nt);
+        const int cols_pad = l->lay.passes * (1 << l->lay.g_r_log2) * l->lay.U;
+        const long long slots = (long long)l->lay.brows * (1 << l->lay.g_k_log2) * cols_pad;
+        const unsigned nt = 128, nb = (unsigned)((slots + nt - 1) / nt);
         if (l->dtype == QKAN_COMPLEX64)
-            qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, (CS<float>*)l->wtab, l->xidx,
-                                                                           l->counters + 1);
+            qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, cols_pad, slots,
+                                                                           (BlockRec<float>*)l->wtab, l->counters + 1);
         else
-            qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, (CS<double>*)l->wtab, l->xidx,
-                                                                            l->counters + 1);
+            qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, cols_pad, slots,
+                                                                            (BlockRec<double>*)l->wtab, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);
     const unsigned nt = 128, nb = (nab + nt - 1) / nt;
@@ -232,12 +236,14 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
 static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream) {
     if (l->engine == 0) {
         BlockParams p;
-        p.x = x; p.wtab = l->wtab; p.xitab = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
+        p.x = x; p.rec = l->wtab; p.out = out; p.amps = amps; p.oor = l->counters;
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
-        p.rowlen = l->N * (l->D + 1);
+        p.cols_pad = l->lay.passes * (1 << l->lay.g_r_log2) * l->lay.U;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
         p.sub = 1; p.tma_ok = 0;
+        for (int q = 0; q < 8; ++q) p.init[q] = 0.0;
+        p.init[0] = 1.0;                                   // PREPARE'd block state (1, 0, 0, 0), un-normalised
         p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
         p.amp_scale = pow(2.0, -0.5 * (double)(l->NA + l->NB + 2 * l->L + l->NA));
         cudaError_t e = l->bkern->launch(p, 1 << (l->lay.g_r_log2 + l->lay.g_k_log2), l->sm_count, stream, &l->last_grid,
@@ -369,11 +375,12 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         info->min_ctas_per_sm = k.MINB;
         info->samples_per_cta = k.NT / G;
         info->passes_exec = l->D + 1;
-        // per live block: D rotations of two complex pairs (2 x (4 DMUL + 4 DFMA) = 24 flops, 16 instructions),
-        // the SELECT rotation pruned to its (0,0) output (2 DMUL + 2 DFMA = 6 flops, 4 instructions) and one
-        // complex add into the read-out sum (2 flops, 2 instructions)
-        info->flops_exec = cf * (double)info->blocks * (24.0 * l->D + 8.0);
-        info->fp_inst_exec = cf * (double)info->blocks * (16.0 * l->D + 6.0);
+        // per live block (see evolve_blocks): D-1 full CHEB passes (16 instr / 24 flops), the last CHEB pass
+        // and the SELECT rotation pruned to the light cone of the read-out (8 + 4 instr / 12 + 6 flops), one
+        // complex add (2 / 2).  DFMA = 2 flops, DMUL = DADD = 1.
+        const double Dd = (double)l->D;
+        info->flops_exec = cf * (double)info->blocks * (l->D > 0 ? 24.0 * Dd - 4.0 : 8.0);
+        info->fp_inst_exec = cf * (double)info->blocks * (l->D > 0 ? 16.0 * Dd - 2.0 : 6.0);
         info->layout_efficiency = l->lay.efficiency;
     } else {
         const KernelInfo& k = *l->kern;

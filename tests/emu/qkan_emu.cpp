@@ -110,20 +110,20 @@ template <class A, typename R, int U, int MODE>
 int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, double* out, double* amps) {
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
     if (lay.U != U) return -3;
-    const int rowlen = N * (D + 1);
-    const long long E = (long long)K * rowlen;
-    std::vector<CS<R>> wtab(E);
-    std::vector<int> xitab(E);
-    for (long long e = 0; e < E; ++e) fill_block_entry<R>(e, W, N, K, D, wtab.data(), xitab.data());
     const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2;
+    const int cols_pad = lay.passes * G_r * U;
+    const long long slots = (long long)lay.brows * G_k * cols_pad;
+    std::vector<BlockRec<R>> rec(slots);
+    for (long long e = 0; e < slots; ++e) fill_block_rec<R>(e, W, N, K, D, cols_pad, rec.data());
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
     while ((1 << NB) < K) ++NB;
     while ((1 << L) < D + 1) ++L;
     const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
     for (long long s = 0; s < B; ++s) {
-        std::vector<CS<R>> cs(N);
+        std::vector<CS<R>> cs(N + 1);
         for (int n = 0; n < N; ++n) { R c = clip_unit<R>(x[s * N + n]); cs[n].c = c; cs[n].s = qk_sqrt((R(1) - c) * (R(1) + c)); }
+        cs[N].c = 0; cs[N].s = 1;
         for (int bi = 0; bi < lay.brows; ++bi)
             for (int k = 0; k < G_k; ++k) {
                 const int b = bi * G_k + k;
@@ -133,20 +133,16 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                     for (int pi = 0; pi < lay.passes; ++pi) {
                         R cx[U], sx[U], cw[U], sw[U];
                         int deg[U];
+                        const BlockRec<R>* rp = rec.data() + (size_t)b * cols_pad + ((size_t)pi * G_r + r) * U;
                         for (int u = 0; u < U; ++u) {
-                            const int i = (pi * U + u) * G_r + r;
-                            const bool live = b < K && i < rowlen;
-                            cw[u] = 0; sw[u] = 1; cx[u] = 0; sx[u] = 1; deg[u] = 0;
-                            if (live) {
-                                const long long e = (long long)b * rowlen + i;
-                                cw[u] = wtab[e].c; sw[u] = wtab[e].s;
-                                const int xi = xitab[e] & 0xFFFFF;
-                                deg[u] = xitab[e] >> 20;
-                                cx[u] = cs[xi].c; sx[u] = cs[xi].s;
-                            }
+                            cw[u] = rp[u].c; sw[u] = rp[u].s; deg[u] = rp[u].deg;
+                            const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + rp[u].xoff);
+                            cx[u] = e.c; sx[u] = e.s;
                         }
-                        A part = evolve_blocks<A, R, U, MODE>(cx, sx, cw, sw, deg, D);
-                        add_amp(acc[r], part);
+                        A init[4];
+                        for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
+                        A part = evolve_blocks<A, R, U, MODE>(init, cx, sx, cw, sw, deg, D);
+                        if (lay.passes == 1) acc[r] = part; else add_amp(acc[r], part);
                     }
                 }
                 for (int m = G_r >> 1; m >= 1; m >>= 1) {

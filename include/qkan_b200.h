@@ -106,11 +106,21 @@ int qkan_layer_info(qkan_layer* layer, qkan_kernel_info* info);
 int qkan_forward(const void* x, const void* w, void* out, int64_t B, int N, int K, int D,
                  int dtype, int mode, void* amps, void* cuda_stream);
 
+/* Gate-list statevector simulation (what the reference's unit tests do with Qiskit Aer's
+ * unitary_simulator: MulStep.py:115-166, LCUStep.py:69-107, SUMStep.py:40-78).  Device pointers.
+ *   gates   int[n_gates][3] = {kind, q0, q1}; kind 0 H(q0), 1 RY(q0, params[g]), 2 CX(control q0, target q1),
+ *           3 SWAP(q0, q1), 4 X(q0), 5 Z(q0); qubit 0 = least significant bit of the amplitude index
+ *   basis   int64[n_states]: initial basis state of each run
+ *   state_out complex128 [n_states, 2^n_qubits]: evolved states (row j = column `basis[j]` of the unitary) */
+int qkan_simulate_circuit(const int* gates, const double* params, int n_gates, int n_qubits,
+                          const long long* basis, int64_t n_states, void* state_out, void* cuda_stream);
+
 /* Measured peaks used as roofline denominators: dependent-free FMA chains on every SM.
  * fp64 != 0: DFMA, else FFMA.  Returns TFLOP/s (2 flops per FMA). */
 int qkan_measure_fma_peak(int device, int fp64, double* tflops);
 
 const char* qkan_last_error(void);
+int qkan_set_last_error(const char* msg);   /* internal: lets the other translation units report */
 void qkan_version(int* major, int* minor, int* patch);
 
 #ifdef __cplusplus

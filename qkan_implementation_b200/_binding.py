@@ -21,7 +21,8 @@ PREPS = {"analytic": 1, "gates": 0}
 EXPORTS = [
     "qkan_layer_create", "qkan_layer_destroy", "qkan_layer_set_weights", "qkan_layer_forward",
     "qkan_layer_forward_host", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals",
-    "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version",
+    "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version", "qkan_simulate_circuit",
+    "qkan_set_last_error",
 ]
 
 
@@ -70,6 +71,7 @@ def lib():
     L.qkan_layer_info.argtypes = [vp, ctypes.POINTER(KernelInfo)]
     L.qkan_layer_diagonals.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     L.qkan_forward.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
+    L.qkan_simulate_circuit.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
     L.qkan_measure_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.qkan_last_error.restype = ctypes.c_char_p
     L.qkan_version.argtypes = [ctypes.POINTER(i32)] * 3

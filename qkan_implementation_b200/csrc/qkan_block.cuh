@@ -82,6 +82,7 @@ struct BlockParams {
     int brows;                  // ceil(K / G_k)
     int sub;                    // sub-iterations per x tile
     int tma_ok;
+    int direct_x;               // wide input rows: no raw-x staging buffers, the pre-pass reads x from global memory
     double out_scale, amp_scale;
     double init[8];             // prepared block state, 4 complex amplitudes (re, im): (1,0,0,0) un-normalised
 };
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int tile = SPC * p.sub;                            // samples per x tile
     const int NP = p.N + 1;                                  // cs row: N rotation pairs + the dummy (0, 1)
     // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (clip + sqrt of the current tile) | mbar[2]
-    const size_t xs_doubles = ((size_t)tile * p.N + 1) & ~(size_t)1;
+    const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
     double* xs0 = reinterpret_cast<double*>(smem_raw);
     CS<R>* cs = reinterpret_cast<CS<R>*>(smem_raw + 2 * xs_doubles * sizeof(double));
     unsigned long long* mbar =
@@ -254,6 +255,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     // stage the x rows of tile `it` into buffer b: one 1-D TMA bulk copy when the tile is 16-byte
     // granular, plain coalesced loads otherwise (ragged tail, odd N)
     auto issue_x = [&](long long it, int b) {
+        if (p.direct_x) return;
         const unsigned bytes = tile_bytes(it);
         const double* src = p.x + it * tile * p.N;
         double* dst = xs0 + (size_t)b * xs_doubles;
@@ -305,12 +307,12 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const long long out_stride = (long long)SPC * p.K;
 
     for (; it < n_it; it += gridDim.x, buf ^= 1) {
-        if (p.tma_ok && (tile_bytes(it) & 15u) == 0) {
+        if (!p.direct_x && p.tma_ok && (tile_bytes(it) & 15u) == 0) {
             if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
         }
-        const double* xs = xs0 + (size_t)buf * xs_doubles;
         const long long s0 = it * tile;
+        const double* xs = p.direct_x ? p.x + s0 * p.N : xs0 + (size_t)buf * xs_doubles;
         const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
 
         // pre-pass over the raw inputs of the tile: range count (the reference prints a warning,
@@ -432,9 +434,12 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, RESIDENT, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
+    // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
+    // halve the resident warps; the per-tile compute is long, so the pre-pass reads global memory directly
+    p.direct_x = ((size_t)SPC * p.N * 16 > 16 * 1024) ? 1 : 0;
     auto smem_for = [&](int sub) {
         const size_t tile = (size_t)SPC * sub;
-        const size_t xs = 2 * ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
+        const size_t xs = p.direct_x ? 0 : 2 * ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
         const size_t cs = (tile * (p.N + 1) * sizeof(CS<R>) + 15) & ~(size_t)15;
         return xs + cs + 16;
     };

@@ -98,16 +98,24 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB" (0 = any)
         int fU = 0, fNT = 0, fMINB = 0;
         if (tune) sscanf(tune, "%d:%d:%d", &fU, &fNT, &fMINB);
-        const size_t per_x = 16 + 2 * amp_real_size(dtype);      // two raw x buffers + the (cos, sin) pair
+        const size_t per_x = 2 * amp_real_size(dtype);           // the (cos, sin) pair (wide rows skip the raw-x staging)
         const int NTs[4] = {256, 128, 64, 32};
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
             const int NT = NTs[ni];
             if (fNT && NT != fNT) continue;
             for (int min_g = 0; min_g <= 5 && !bbest; ++min_g) {
-                const BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
-                const int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
+                BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
+                int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                 if (G < (1 << min_g) || G > NT) continue;
-                if ((size_t)(NT / G) * (N + 1) * per_x > 72 * 1024) continue;
+                const size_t cs_bytes = (size_t)(NT / G) * (N + 1) * per_x;
+                if (cs_bytes > 72 * 1024) continue;
+                // wide input rows: shared memory limits the resident warps (< 24 per SM), so keep four blocks
+                // per lane in flight instead of one (measured on N784 K10 D5: 3.7 -> 4.0 M samples/s)
+                if (!fU && (220 * 1024 / (cs_bytes + 1024)) * (size_t)(NT / 32) < 24) {
+                    const BlockLayout wide = plan_block_layout(N, K, max_degree, min_g, 4);
+                    const int Gw = 1 << (wide.g_r_log2 + wide.g_k_log2);
+                    if (Gw == G) cand = wide;
+                }
                 const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
                     if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
@@ -247,7 +255,7 @@ static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, voi
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
-        p.sub = 1; p.tma_ok = 0;
+        p.sub = 1; p.tma_ok = 0; p.direct_x = 0;
         for (int q = 0; q < 8; ++q) p.init[q] = 0.0;
         p.init[0] = 1.0;                                   // PREPARE'd block state (1, 0, 0, 0), un-normalised
         p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
@@ -520,6 +528,7 @@ extern "C" int qkan_measure_fma_peak(int device, int fp64, double* tflops) {
 }
 
 extern "C" const char* qkan_last_error(void) { return g_last_error.c_str(); }
+extern "C" int qkan_set_last_error(const char* msg) { g_last_error = msg ? msg : ""; return 0; }
 extern "C" void qkan_version(int* major, int* minor, int* patch) {
     if (major) *major = 0;
     if (minor) *minor = 1;

@@ -83,6 +83,11 @@ struct BlockParams {
     int sub;                    // sub-iterations per x tile
     int tma_ok;
     int direct_x;               // wide input rows: no raw-x staging buffers, the pre-pass reads x from global memory
+    // derived launch constants (filled by launch_block; kept in the constant bank so that the kernel does
+    // not spend registers or instructions on them)
+    int G, G_r, G_k;            // lanes per sample / per row / rows in parallel
+    int SPC, tile;              // samples in flight per CTA; samples per x tile (SPC * sub)
+    int pre_log2;               // pre-pass: 2^pre_log2 threads share one input row (>= min(N, 32), no division)
     double out_scale, amp_scale;
     double init[8];             // prepared block state, 4 complex amplitudes (re, im): (1,0,0,0) un-normalised
 };
@@ -212,11 +217,9 @@ template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) 
 template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT, int DT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int G = 1 << (p.g_r_log2 + p.g_k_log2);
-    const int G_r = 1 << p.g_r_log2;
-    const int G_k = 1 << p.g_k_log2;
-    const int SPC = NT / G;                                  // samples in flight per CTA
-    const int tile = SPC * p.sub;                            // samples per x tile
+    const int G = p.G, G_r = p.G_r, G_k = p.G_k;
+    const int SPC = p.SPC;                                   // samples in flight per CTA
+    const int tile = p.tile;                                 // samples per x tile
     const int NP = p.N + 1;                                  // cs row: N rotation pairs + the dummy (0, 1)
     // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (clip + sqrt of the current tile) | mbar[2]
     const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
@@ -319,15 +322,22 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         // ChebyshevStep.py:46-49), clip (:52) and the rotation pair cos(theta/2) = x,
         // sin(theta/2) = sqrt(1 - x^2) - no arccos is ever needed
         unsigned bad = 0;
-        for (int i = tid; i < nsamp * p.N; i += NT) {
-            const double v = xs[i];
-            if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
-            const R c = clip_unit<R>(v);
-            CS<R> e;
-            e.c = c;
-            e.s = qk_sqrt((R(1) - c) * (R(1) + c));
-            const int row = i / p.N;
-            cs[i + row] = e;                                  // row stride N + 1
+        {
+            const int gs = 1 << p.pre_log2;                   // threads per input row
+            const int n0 = tid & (gs - 1);
+            for (int row = tid >> p.pre_log2; row < nsamp; row += NT >> p.pre_log2) {
+                const double* xr = xs + (size_t)row * p.N;
+                CS<R>* cr = cs + (size_t)row * NP;
+                for (int n = n0; n < p.N; n += gs) {
+                    const double v = xr[n];
+                    if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
+                    const R c = clip_unit<R>(v);
+                    CS<R> e;
+                    e.c = c;
+                    e.s = qk_sqrt((R(1) - c) * (R(1) + c));
+                    cr[n] = e;
+                }
+            }
         }
         if (bad) atomicAdd(p.oor, (unsigned long long)bad);
         __syncthreads();                                      // cs complete, xs[buf] free again
@@ -460,6 +470,10 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     if (grid < 1) grid = 1;
     p.sub = sub;
     p.tma_ok = ((reinterpret_cast<uintptr_t>(p.x) & 15u) == 0 && (((size_t)SPC * sub * p.N * 8) & 15u) == 0) ? 1 : 0;
+    p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
+    p.SPC = SPC; p.tile = SPC * sub;
+    p.pre_log2 = 0;
+    while ((1 << p.pre_log2) < p.N && p.pre_log2 < 5) ++p.pre_log2;
     if (grid_out) *grid_out = (int)grid;
     if (smem_out) *smem_out = (int)smem_for(sub);
     kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);

@@ -263,6 +263,32 @@ def run_ours(a):
                        "how": "same step followed by one NCCL all_gather_into_tensor of the [B, K] float64 outputs, cut in 4 chunks "
                               "that overlap with the next chunk's kernel (BASELINE north_star's 'final gather'); not part of `value` "
                               "because the samples shard with no data-path exchange"}
+    fused_line = None
+    if have_gather:
+        fused_line = {}
+        for name, use_mc in (("nvls_multicast", True), ("peer_stores", False)):
+            try:
+                from qkan_implementation_b200 import FusedGatherQKANLayer
+                fused = FusedGatherQKANLayer(layer, multicast=use_mc)
+                full = [None]
+
+                def step_fused():
+                    full[0] = fused.forward(xd, Wl, world * B)
+                    return 1
+                fsteps = max(3, min(a.steps, 50))
+                f_ms, _, _, _ = timed(step_fused, fsteps, 3)
+                # check: the gathered result equals, bitwise, what every rank computed on its own slice
+                ref_list = [torch.empty_like(outs[0]) for _ in range(world)]
+                dist.all_gather(ref_list, outs[0])
+                same_all = bool(torch.equal(full[0], torch.cat(ref_list, dim=0)))
+                fused_line[name] = {"value": world * B * fsteps / (f_ms * 1e-3), "unit": "samples/s", "ms_per_step": f_ms / fsteps,
+                                    "steps": fsteps, "path": fused.last_path, "bitwise_equal_to_sharded": same_all}
+            except Exception as e:      # noqa: BLE001  (report, do not hide: the sharded value above is unaffected)
+                fused_line[name] = {"error": f"{type(e).__name__}: {e}"}
+        fused_line["how"] = ("the kernel itself delivers every result row to every rank: nvls_multicast = one multimem.st per result "
+                             "through the NVSwitch multicast mapping of the [B_total, K] buffer (qkan_layer_forward_multicast); peer_stores = "
+                             "one plain store per rank over NVLink peer mappings (qkan_layer_forward_peers); then one symmetric-memory "
+                             "barrier; no NCCL collective in the step")
     do_gather = False
 
     # ---- end-to-end through the public API with pinned host buffers
@@ -348,7 +374,7 @@ def run_ours(a):
                 "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": world * B, "mode": a.mode, "prep": a.prep,
                            "l2": "flushed between timed steps (256 MiB device write)",
                            "sharding": "contiguous batch slice per rank, weights replicated, no data-path collective", "kernel": info},
-                "clocks": clocks, "e2e": e2e, "with_output_gather": gather_line, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "with_output_gather": gather_line, "with_fused_peer_gather": fused_line, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:

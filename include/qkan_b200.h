@@ -61,6 +61,20 @@ int qkan_layer_set_weights(qkan_layer* layer, const double* W, int on_device, in
  * Asynchronous on cuda_stream (a cudaStream_t, NULL = default stream). */
 int qkan_layer_forward(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps, void* cuda_stream);
 
+/* Forward fused with the output gather of a multi-GPU run: rows [row_offset, row_offset + B)
+ * of the full result are stored by the kernel itself into EVERY buffer of out_ptrs - out_ptrs[0] is the
+ * local [B_total, K] float64 buffer, the others are the same buffer of the NVLink peers mapped into this
+ * process (e.g. torch symmetric memory) - so the transfer overlaps the arithmetic store by store and no
+ * separate collective runs.  The caller synchronises the ranks afterwards (barrier).  Block engine only. */
+int qkan_layer_forward_peers(qkan_layer* layer, const double* x, int64_t B, void* const* out_ptrs, int n_ptrs,
+                             int64_t row_offset, void* cuda_stream);
+
+/* The same through an NVLink multicast (NVLS) mapping of the result buffer: mc_out is the multicast address of
+ * the [B_total, K] buffer (e.g. torch symmetric memory's multicast_ptr); the kernel issues ONE multimem.st per
+ * result and the NVSwitch replicates it into every rank's memory, the local one included. */
+int qkan_layer_forward_multicast(qkan_layer* layer, const double* x, int64_t B, void* mc_out, int64_t row_offset,
+                                 void* cuda_stream);
+
 /* Same call with HOST buffers (pinned memory recommended): the batch is cut in chunks and
  * H2D copy, kernel and D2H copy of consecutive chunks overlap on three streams.
  * Synchronous: returns when `out` (and `amps`) are complete. */

@@ -11,7 +11,7 @@ All arithmetic runs in ``libqkan_b200.so`` (hand-written sm_100a CUDA behind the
 """
 from .layer import ChebyshevStep, LCUStep, MulStep, QKANLayer, SUMStep
 from . import _binding
-from .distributed import ShardedQKANLayer, shard_bounds
+from .distributed import FusedGatherQKANLayer, ShardedQKANLayer, shard_bounds
 
-__all__ = ["ChebyshevStep", "MulStep", "LCUStep", "SUMStep", "QKANLayer", "ShardedQKANLayer", "shard_bounds"]
+__all__ = ["ChebyshevStep", "MulStep", "LCUStep", "SUMStep", "QKANLayer", "ShardedQKANLayer", "FusedGatherQKANLayer", "shard_bounds"]
 __version__ = "0.1.0"

@@ -20,7 +20,7 @@ PREPS = {"analytic": 1, "gates": 0}
 
 EXPORTS = [
     "qkan_layer_create", "qkan_layer_destroy", "qkan_layer_set_weights", "qkan_layer_forward",
-    "qkan_layer_forward_host", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals",
+    "qkan_layer_forward_host", "qkan_layer_forward_peers", "qkan_layer_forward_multicast", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals",
     "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version", "qkan_simulate_circuit",
     "qkan_set_last_error",
 ]
@@ -67,6 +67,8 @@ def lib():
     L.qkan_layer_set_weights.argtypes = [vp, vp, i32, i32, vp]
     L.qkan_layer_forward.argtypes = [vp, vp, i64, vp, vp, vp]
     L.qkan_layer_forward_host.argtypes = [vp, vp, i64, vp, vp]
+    L.qkan_layer_forward_peers.argtypes = [vp, vp, i64, ctypes.POINTER(vp), i32, i64, vp]
+    L.qkan_layer_forward_multicast.argtypes = [vp, vp, i64, vp, i64, vp]
     L.qkan_layer_out_of_range.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64)]
     L.qkan_layer_info.argtypes = [vp, ctypes.POINTER(KernelInfo)]
     L.qkan_layer_diagonals.argtypes = [vp, vp, i64, vp, vp, vp, vp]

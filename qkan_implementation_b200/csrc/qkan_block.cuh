@@ -72,8 +72,13 @@ struct BlockParams {
     const void* cstab;          // CS<R>[slots + U*G]: SELECT rotation (cos, sin)(theta_w / 2) per block slot
     const int* xotab;           // int[slots + U*G]: byte offset of the CHEB rotation pair in the sample's cs row
                                 //                   (| degree << 24 in paper mode)
-    double* out;                // [B, K]
-    void* amps;                 // optional [B, K] complex
+    double* outs[8];            // [row0 + B, K] result buffers: outs[0] is local; outs[1..n_out) are the same buffer
+                                // of the NVLink peers (fused output gather: every result is stored to every rank)
+    int n_out;
+    double* mc_out;             // optional NVLink-multicast (NVLS) mapping of the result buffer: one multimem.st per
+                                // result is replicated to every rank by the NVSwitch (then outs[] is not written)
+    long long row0;             // first row of this rank's slice in the result buffers
+    void* amps;                 // optional [B, K] complex (local only)
     unsigned long long* oor;
     long long B;
     int N, K, D;
@@ -204,6 +209,15 @@ QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], co
 }
 
 #if defined(__CUDACC__)
+// result store: to every listed buffer (local + NVLink peers), or once through the multicast mapping
+__device__ __forceinline__ void store_result(const BlockParams& p, long long idx, double val) {
+    if (p.mc_out != nullptr) {
+        asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p.mc_out + idx), "d"(val) : "memory");
+    } else {
+        for (int q = 0; q < p.n_out; ++q) p.outs[q][idx] = val;
+    }
+}
+
 template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) {
     A r;
     r.re = __shfl_xor_sync(0xffffffffu, a.re, m);
@@ -346,9 +360,10 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 
         const int nsub = (nsamp + SPC - 1) / SPC;
         const char* csrow = reinterpret_cast<const char*>(cs) + (size_t)slot * NP * sizeof(CS<R>);
-        long long o = (s0 + slot) * p.K;
+        long long o = (p.row0 + s0 + slot) * p.K;
+        long long oa = (s0 + slot) * p.K;                     // amps are local: no row offset
         int ls = slot;
-        for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, ls += SPC) {
+        for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, oa += out_stride, ls += SPC) {
             const bool valid = ls < nsamp;
             const char* row = valid ? csrow : reinterpret_cast<const char*>(cs);   // idle slots of a ragged tile read row 0
             if constexpr (RESIDENT) {
@@ -363,13 +378,14 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                 // row's blocks, finished across the G_r lanes with an xor butterfly
                 for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
                 if (valid && r == 0 && k < p.K) {
-                    p.out[o + k] = (double)acc.re * p.out_scale;
+                    const double val = (double)acc.re * p.out_scale;
+                    store_result(p, o + k, val);
                     if (p.amps) {
                         Cplx<R> z;
                         z.re = (R)((double)acc.re * p.amp_scale);
                         if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
                         else z.im = R(0);
-                        reinterpret_cast<Cplx<R>*>(p.amps)[o + k] = z;
+                        reinterpret_cast<Cplx<R>*>(p.amps)[oa + k] = z;
                     }
                 }
             } else {
@@ -402,13 +418,14 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     }
                     for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
                     if (valid && r == 0 && b < p.K) {
-                        p.out[o + b] = (double)acc.re * p.out_scale;
+                        const double val = (double)acc.re * p.out_scale;
+                        store_result(p, o + b, val);
                         if (p.amps) {
                             Cplx<R> z;
                             z.re = (R)((double)acc.re * p.amp_scale);
                             if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
                             else z.im = R(0);
-                            reinterpret_cast<Cplx<R>*>(p.amps)[o + b] = z;
+                            reinterpret_cast<Cplx<R>*>(p.amps)[oa + b] = z;
                         }
                     }
                 }

@@ -248,10 +248,17 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
     return QKAN_OK;
 }
 
-static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream) {
+static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, cudaStream_t stream,
+                     void* const* peer_outs = nullptr, int n_peers = 0, int64_t row0 = 0, void* mc_out = nullptr) {
     if (l->engine == 0) {
         BlockParams p;
-        p.x = x; p.cstab = l->wtab; p.xotab = l->xidx; p.out = out; p.amps = amps; p.oor = l->counters;
+        p.x = x; p.cstab = l->wtab; p.xotab = l->xidx; p.amps = amps; p.oor = l->counters;
+        for (int q = 0; q < 8; ++q) p.outs[q] = nullptr;
+        p.outs[0] = out; p.n_out = 1; p.row0 = row0; p.mc_out = (double*)mc_out;
+        if (peer_outs) {
+            p.n_out = n_peers;
+            for (int q = 0; q < n_peers; ++q) p.outs[q] = (double*)peer_outs[q];
+        }
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
@@ -312,6 +319,33 @@ static int ensure_host_path(qkan_layer* l, int64_t B, bool want_amps) {
         l->cap_amps = B;
     }
     return QKAN_OK;
+}
+
+extern "C" int qkan_layer_forward_peers(qkan_layer* l, const double* x, int64_t B, void* const* out_ptrs, int n_ptrs,
+                                        int64_t row_offset, void* cuda_stream) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0 || row_offset < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch / row offset");
+    if (!out_ptrs || n_ptrs < 1 || n_ptrs > 8) return fail(QKAN_ERR_BAD_SHAPE, "need 1..8 result buffers");
+    for (int q = 0; q < n_ptrs; ++q) if (!out_ptrs[q]) return fail(QKAN_ERR_BAD_SHAPE, "null result buffer");
+    if (l->engine != 0) return fail(QKAN_ERR_UNSUPPORTED, "the fused output gather is implemented by the block engine (prep = analytic)");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
+    CU(cudaSetDevice(l->device));
+    return launch_on(l, x, B, (double*)out_ptrs[0], nullptr, (cudaStream_t)cuda_stream, out_ptrs, n_ptrs, row_offset);
+}
+
+extern "C" int qkan_layer_forward_multicast(qkan_layer* l, const double* x, int64_t B, void* mc_out, int64_t row_offset,
+                                            void* cuda_stream) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0 || row_offset < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch / row offset");
+    if (!mc_out) return fail(QKAN_ERR_BAD_SHAPE, "null multicast pointer");
+    if (l->engine != 0) return fail(QKAN_ERR_UNSUPPORTED, "the fused output gather is implemented by the block engine (prep = analytic)");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
+    CU(cudaSetDevice(l->device));
+    return launch_on(l, x, B, nullptr, nullptr, (cudaStream_t)cuda_stream, nullptr, 0, row_offset, mc_out);
 }
 
 extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B, double* out, void* amps) {

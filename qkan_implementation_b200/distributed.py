@@ -47,6 +47,60 @@ def gather_outputs(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
     return torch.cat([full[r * mx: r * mx + sizes[r]] for r in range(world)], dim=0)
 
 
+class FusedGatherQKANLayer:
+    """Multi-GPU forward whose output gather is fused into the kernel: every rank's kernel stores its
+    rows straight into the result buffer of every NVLink peer (torch symmetric memory gives the peer
+    mappings), so there is no separate collective and the transfer overlaps the arithmetic.  After
+    ``forward`` (which ends with a symmetric-memory barrier) every rank holds the full ``[B, K]``.
+
+    One process per GPU, NCCL process group initialised, CUDA ``QKANLayer`` with ``prep="analytic"``."""
+
+    def __init__(self, layer, group=None, multicast: bool = True):
+        self.layer = layer
+        self.group = group if group is not None else dist.group.WORLD
+        self.multicast = multicast          # use the NVSwitch multicast mapping when the fabric offers one
+        self._bufs = {}
+
+    def _buffer(self, B: int, K: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        key = (B, K)
+        if key not in self._bufs:
+            t = symm_mem.empty((B, K), dtype=torch.float64, device=device)
+            hdl = symm_mem.rendezvous(t, self.group)
+            self._bufs[key] = (t, hdl)
+        return self._bufs[key]
+
+    def forward(self, x_local: torch.Tensor, weights, B_total: int, barrier: bool = True) -> torch.Tensor:
+        """x_local: this rank's contiguous slice (shard_bounds) as a CUDA tensor [B_local, N]."""
+        import ctypes
+        from . import _binding as _b
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = shard_bounds(B_total, world, rank)
+        if x_local.shape[0] != hi - lo:
+            raise ValueError(f"rank {rank} expects {hi - lo} rows, got {x_local.shape[0]}")
+        if world > 8:
+            raise ValueError("the fused gather addresses at most 8 peers (one NVSwitch box)")
+        eng = self.layer._engine
+        self.layer._set_weights(weights)
+        out, hdl = self._buffer(B_total, self.layer.K, x_local.device)
+        xd = x_local.to(torch.float64).contiguous()
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if self.multicast else 0
+        self.last_path = "multicast" if mc else "peer-stores"
+        if mc:
+            # one multimem.st per result, replicated to every rank (this one included) by the NVSwitch
+            _b.check(_b.lib().qkan_layer_forward_multicast(eng.handle(), xd.data_ptr(), xd.shape[0], ctypes.c_void_p(mc), lo,
+                                                           eng._stream_ptr()))
+        else:
+            # own buffer first, then the peers
+            order = [rank] + [r for r in range(world) if r != rank]
+            ptrs = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(hdl.buffer_ptrs[r])) for r in order])
+            _b.check(_b.lib().qkan_layer_forward_peers(eng.handle(), xd.data_ptr(), xd.shape[0], ptrs, world, lo,
+                                                       eng._stream_ptr()))
+        if barrier:
+            hdl.barrier()          # every rank's kernel has finished: all rows of all ranks are in place
+        return out
+
+
 class ShardedQKANLayer:
     """One process per GPU; `forward` takes the FULL batch description and computes this
     rank's slice.  ``compute`` is the per-rank callable (the CUDA QKANLayer on a GPU box;

@@ -230,6 +230,32 @@ def test_c_abi_direct(Q):
     assert b.measure_fma_peak(0, True) > 5.0
 
 
+def test_c_abi_forward_peers_multi_store(Q):
+    """fused output gather: the kernel stores each row into every listed buffer at the rank's row offset
+    (here two buffers on the same GPU stand in for NVLink peers)"""
+    b = Q._binding
+    lib = b.lib()
+    N, K, D, B = 8, 8, 4, 3001
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.uniform(-1, 1, (B, N))).cuda()
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    layer = Q.QKANLayer(N, K, D)
+    y = layer.forward(x, W)
+    row0, Btot = 517, 5000
+    bufs = [torch.full((Btot, K), 7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+    ptrs = (ctypes.c_void_p * 3)(*[ctypes.c_void_p(t.data_ptr()) for t in bufs])
+    rc = lib.qkan_layer_forward_peers(layer._engine.handle(), x.data_ptr(), B, ptrs, 3, row0, None)
+    assert rc == 0, lib.qkan_last_error()
+    torch.cuda.synchronize()
+    for t in bufs:
+        assert torch.equal(t[row0:row0 + B], y)
+        assert float(t[:row0].min()) == 7.0 and float(t[row0 + B:].max()) == 7.0      # nothing else touched
+    assert lib.qkan_layer_forward_peers(layer._engine.handle(), x.data_ptr(), B, ptrs, 9, row0, None) == b.ERR_BAD_SHAPE
+    gates = Q.QKANLayer(N, K, D, prep="gates")
+    gates.forward(x[:4], W)
+    assert lib.qkan_layer_forward_peers(gates._engine.handle(), x.data_ptr(), B, ptrs, 1, 0, None) == b.ERR_UNSUPPORTED
+
+
 # ------------------------------------------------- full-size, size-independent properties
 @pytest.mark.parametrize("N,K,D,B", [(4, 4, 3, 1_000_000),        # BASELINE configs[1]
                                      (16, 16, 8, 1_000_000),     # configs[2]

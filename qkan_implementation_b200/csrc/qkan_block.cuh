@@ -225,10 +225,9 @@ template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) 
     return r;
 }
 
-// RESIDENT: every block slot of the layer has its own (lane, u) (one pass, one row step), so the
-// records stay in registers for the whole launch and the per-sample body is straight-line code.
-// Otherwise the lane streams its records pass by pass (coalesced, L1/L2 resident).
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT, int DT>
+// SIMPLE: every lane owns one whole output row of its sample (G_r = 1 and a single row step - the
+// layout of every small BASELINE layer): no row loop and no shuffle step in the per-sample code.
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool SIMPLE, int DT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int G = p.G, G_r = p.G_r, G_k = p.G_k;
@@ -301,16 +300,11 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         if constexpr (MODE == 1) { xoff[u] = xo & 0xFFFFFF; deg[u] = xo >> 24; }
         else { xoff[u] = xo; deg[u] = 0; }
     };
-    // entries of the first pass: resident for the whole launch (RESIDENT: the only pass), so a new
-    // sample never waits for a table load
+    // entries of the first pass: resident for the whole launch, so a new sample never waits for a table load
     CS<R> q0[U];
     int x0[U];
     QK_UNROLL
     for (int u = 0; u < U; ++u) { q0[u] = cstab[(size_t)u * G + g]; x0[u] = xotab[(size_t)u * G + g]; }
-    if constexpr (RESIDENT) {
-        QK_UNROLL
-        for (int u = 0; u < U; ++u) unpack(u, q0[u], x0[u]);
-    }
 
     // two tiles in flight: tile i is consumed while tiles i+1 and (after its pre-pass) i+2 are loading
     long long it = blockIdx.x;
@@ -366,68 +360,58 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, oa += out_stride, ls += SPC) {
             const bool valid = ls < nsamp;
             const char* row = valid ? csrow : reinterpret_cast<const char*>(cs);   // idle slots of a ragged tile read row 0
-            if constexpr (RESIDENT) {
-                R cx[U], sx[U];
-                QK_UNROLL
-                for (int u = 0; u < U; ++u) {
-                    const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
-                    cx[u] = e.c; sx[u] = e.s;
-                }
-                A acc = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
-                // UNPREPARE (H on deg) + SUM (H on a) + post-selection deg = a = 0: the sum over the
-                // row's blocks, finished across the G_r lanes with an xor butterfly
-                for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
-                if (valid && r == 0 && k < p.K) {
-                    const double val = (double)acc.re * p.out_scale;
-                    store_result(p, o + k, val);
-                    if (p.amps) {
-                        Cplx<R> z;
-                        z.re = (R)((double)acc.re * p.amp_scale);
-                        if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
-                        else z.im = R(0);
-                        reinterpret_cast<Cplx<R>*>(p.amps)[oa + k] = z;
+            // stream the lane's slots with one running pointer; the next pass's entries are fetched while
+            // the current pass is evolved (the tables end with one pass of padding slots)
+            const CS<R>* cp = cstab + g;
+            const int* xp = xotab + g;
+            CS<R> qn[U];
+            int xn[U];
+            QK_UNROLL
+            for (int u = 0; u < U; ++u) { qn[u] = q0[u]; xn[u] = x0[u]; }
+            auto run_row = [&]() -> A {
+                A acc;
+                set_amp(acc, 0.0);
+                for (int pi = 0; pi < p.passes; ++pi) {
+                    QK_UNROLL
+                    for (int u = 0; u < U; ++u) unpack(u, qn[u], xn[u]);
+                    cp += (size_t)U * G;
+                    xp += (size_t)U * G;
+                    QK_UNROLL
+                    for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
+                    R cx[U], sx[U];
+                    QK_UNROLL
+                    for (int u = 0; u < U; ++u) {
+                        const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
+                        cx[u] = e.c; sx[u] = e.s;
                     }
+                    const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
+                    add_amp(acc, part);
                 }
+                return acc;
+            };
+            auto write_row = [&](const A& acc, int b) {
+                const double val = (double)acc.re * p.out_scale;
+                store_result(p, o + b, val);
+                if (p.amps) {
+                    Cplx<R> z;
+                    z.re = (R)((double)acc.re * p.amp_scale);
+                    if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
+                    else z.im = R(0);
+                    reinterpret_cast<Cplx<R>*>(p.amps)[oa + b] = z;
+                }
+            };
+            if constexpr (SIMPLE) {
+                // every lane owns one whole output row (G_r = 1, one row step): UNPREPARE + SUM +
+                // post-selection is the lane's running sum, no cross-lane step
+                const A acc = run_row();
+                if (valid && k < p.K) write_row(acc, k);
             } else {
-                // stream the lane's slots with one running pointer; the next pass's entries are fetched
-                // while the current pass is evolved (the tables end with one pass of padding slots)
-                const CS<R>* cp = cstab + g;
-                const int* xp = xotab + g;
-                CS<R> qn[U];
-                int xn[U];
-                QK_UNROLL
-                for (int u = 0; u < U; ++u) { qn[u] = q0[u]; xn[u] = x0[u]; }
                 for (int b = k; b < p.brows * G_k; b += G_k) {
-                    A acc;
-                    set_amp(acc, 0.0);
-                    for (int pi = 0; pi < p.passes; ++pi) {
-                        QK_UNROLL
-                        for (int u = 0; u < U; ++u) unpack(u, qn[u], xn[u]);
-                        cp += (size_t)U * G;
-                        xp += (size_t)U * G;
-                        QK_UNROLL
-                        for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
-                        R cx[U], sx[U];
-                        QK_UNROLL
-                        for (int u = 0; u < U; ++u) {
-                            const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
-                            cx[u] = e.c; sx[u] = e.s;
-                        }
-                        const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
-                        add_amp(acc, part);
-                    }
+                    A acc = run_row();
+                    // UNPREPARE (H on deg) + SUM (H on a) + post-selection deg = a = 0: the sum over the
+                    // row's blocks, finished across the G_r lanes with an xor butterfly
                     for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
-                    if (valid && r == 0 && b < p.K) {
-                        const double val = (double)acc.re * p.out_scale;
-                        store_result(p, o + b, val);
-                        if (p.amps) {
-                            Cplx<R> z;
-                            z.re = (R)((double)acc.re * p.amp_scale);
-                            if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
-                            else z.im = R(0);
-                            reinterpret_cast<Cplx<R>*>(p.amps)[oa + b] = z;
-                        }
-                    }
+                    if (valid && r == 0 && b < p.K) write_row(acc, b);
                 }
             }
         }
@@ -456,9 +440,9 @@ struct BlockKernelInfo {
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
 
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool RESIDENT, int DT>
+template <class A, typename R, int U, int MODE, int NT, int MINB, bool SIMPLE, int DT>
 cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, RESIDENT, DT>;
+    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
@@ -499,7 +483,7 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
 template <class A, typename R, int U, int MODE, int NT, int MINB, int DT>
 cudaError_t launch_block(const BlockParams& p, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
     if (DT > 0 && p.D != DT) return cudaErrorInvalidValue;
-    if (p.passes == 1 && p.brows == 1)
+    if (p.g_r_log2 == 0 && p.brows == 1)
         return launch_block_impl<A, R, U, MODE, NT, MINB, true, DT>(p, G, sm_count, stream, grid_out, smem_out);
     return launch_block_impl<A, R, U, MODE, NT, MINB, false, DT>(p, G, sm_count, stream, grid_out, smem_out);
 }

@@ -200,8 +200,10 @@ class MulStep(ChebyshevStep):
             weights = weights.detach().cpu().numpy()
         if not np.all(np.abs(weights) <= 1):                            # MulStep.py:36-37
             raise ValueError("Weight magnitudes must be <= 1 for unitarity")
-        self._weights[degree] = weights
-        self._version += 1
+        weights = np.asarray(weights, dtype=np.float64)
+        if not np.array_equal(self._weights[degree], weights):          # unchanged rows keep the device tables valid
+            self._weights[degree] = weights
+            self._version += 1
 
     def _engine_for(self, N: int, K: int) -> _Engine:
         eng = self._diag_engines.get((N, K))

@@ -203,6 +203,28 @@ def test_weights_are_stateful_like_reference(Q):
         layer.forward(torch.from_numpy(x).cuda(), Wd * 3)
 
 
+def test_degree_optimizer_predict_pattern(Q):
+    """The hot path's only in-repo caller: DegreeOptimizer.fit builds one-hot weight vectors
+    weights[d][out_idx * N + in_idx] = 1 for the selected degree (DegreeOptimizer.py:63-73) and predict
+    passes a 2-D z-scored array (:89-93) - which raises in the reference for more than one row and is
+    the batched call here; inputs beyond [-1, 1] are clipped like ChebyshevStep.py:52."""
+    rng = np.random.default_rng(21)
+    N, K, D, B = 6, 3, 3, 500
+    degrees = rng.integers(0, D + 1, size=(K, N))
+    weights = [np.zeros(N * K) for _ in range(D + 1)]
+    for out_idx in range(K):
+        for in_idx in range(N):
+            weights[int(degrees[out_idx, in_idx])][out_idx * N + in_idx] = 1.0
+    data = rng.normal(0, 1, (B, N))                                   # z-scored features, |x| > 1 occurs
+    layer = Q.QKANLayer(N, K, D)
+    pred = layer.forward(data, weights, check_range=False)
+    assert pred.shape == (B, K)
+    assert_close(pred, o.forward_closed_form(data, np.array(weights), N, K, D))
+    assert layer.mul_step._weights.shape == (D + 1, N * K)           # what DegreeOptimizer.py:87,327 reads
+    again = layer.forward(data, weights, check_range=False)          # unchanged weights: tables are reused
+    assert np.array_equal(again, pred)
+
+
 # ------------------------------------------------------------------ raw C ABI
 def test_c_abi_direct(Q):
     b = Q._binding

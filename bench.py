@@ -90,7 +90,7 @@ def cpu_reference_rate(a, x, W, per_worker=0, workers=None):
     one = (time.perf_counter() - t0) / 8
     cores = workers or (os.cpu_count() or 1)
     if per_worker <= 0:
-        per_worker = int(max(4, min(20000, 6.0 / max(one, 1e-6))))       # ~6 s of work per worker
+        per_worker = int(max(4, min(100000, 12.0 / max(one, 1e-6))))     # ~12 s of work per worker
     # keep the dense (NK x NK) temporaries of wide layers inside RAM (N=784: ~0.5 GB each)
     mem_per = 4 * 8 * (N * K) ** 2
     cores = max(1, min(cores, int(24e9 // max(mem_per, 1))))
@@ -102,7 +102,7 @@ def cpu_reference_rate(a, x, W, per_worker=0, workers=None):
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return {"value": total / busy, "unit": "samples/s", "cores": cores, "kind": "port",
+    return {"value": total / busy, "unit": "samples/s", "cores": cores, "kind": "port", "wall_s": wall,
             "sample": f"{total} samples ({per_worker}/worker) of the same workload through oracle.forward_reference_style "
                       f"(dense np.diag algebra per sample, like QKANLayer.py:122-135); single-thread {1.0 / one:.1f} samples/s; "
                       f"pool wall {wall:.1f}s"}
@@ -124,7 +124,7 @@ def run_reference(a):
     v = float(np.median(vals))
     base["value"] = v
     line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": base["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_name(a), "note": "CPU port of the reference algorithm (the reference is "
                        "pure Python and cannot travel to the GPU box); each step = a bounded sample of the workload"},

@@ -99,6 +99,7 @@ typedef struct {
     /* block engine */
     int blocks;                 /* N*K*(D+1) live four-amplitude (f_x, f_w) blocks per sample             */
     int unroll;                 /* U: blocks (4U amplitudes) per lane in registers                        */
+    int samples_per_lane;       /* SU: samples a lane evolves at a time (they share every table entry)    */
     int lanes_per_sample, lanes_per_row, rows_in_parallel, passes, row_steps;
     /* staged engine */
     int tile_qubits, tile_na, tile_nb, local_qubits, stages, sectors_total, sectors_run;

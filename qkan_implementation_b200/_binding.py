@@ -29,7 +29,7 @@ EXPORTS = [
 class KernelInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int) for n in
                 ("engine", "n_a", "n_b", "l", "qubits",
-                 "blocks", "unroll", "lanes_per_sample", "lanes_per_row", "rows_in_parallel", "passes", "row_steps",
+                 "blocks", "unroll", "samples_per_lane", "lanes_per_sample", "lanes_per_row", "rows_in_parallel", "passes", "row_steps",
                  "tile_qubits", "tile_na", "tile_nb", "local_qubits", "stages", "sectors_total", "sectors_run",
                  "threads_per_cta", "min_ctas_per_sm", "samples_per_cta", "grid", "smem_bytes",
                  "passes_survey", "passes_exec")] + \

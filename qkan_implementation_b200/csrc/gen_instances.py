@@ -61,33 +61,33 @@ def instances():
     return out
 
 
-# block engine (default): (U, NT) -> MINB options; the first one is the default
+# block engine (default): (U, SU, NT) -> occupancy target (min CTAs per SM).
+# U = blocks per lane in registers (1 by default, 4 when shared memory limits the resident warps),
+# SU = samples per lane at a time (2 for D <= 4).  Chosen from profiles/r01_tune_block_engine_v*.jsonl.
 BLOCK_MINB = {
-    (4, 256): [2], (4, 128): [4], (4, 64): [8], (4, 32): [16],
-    (2, 256): [3], (2, 128): [6], (2, 64): [12], (2, 32): [16],
-    (1, 256): [4, 3], (1, 128): [8, 6], (1, 64): [16], (1, 32): [32],
+    (4, 1, 256): 2, (4, 1, 128): 4, (4, 1, 64): 8, (4, 1, 32): 16,
+    (2, 1, 256): 3, (2, 1, 128): 6,
+    (1, 1, 256): 4, (1, 1, 128): 8, (1, 1, 64): 16, (1, 1, 32): 32,
+    (1, 2, 256): 3, (1, 2, 128): 6,
 }
 DT_MAX = 16     # compile-time degree specialisations (compat mode): D = 1 .. DT_MAX
+SU2_DT_MAX = 4  # two samples per lane only pay off for shallow sequences
 
 
 def block_instances():
-    out = []   # (group, amp, U, MODE, NT, MINB, DT, is_default)
+    out = []   # (group, amp, U, SU, MODE, NT, MINB, DT, is_default)
     for amp in ("c128", "c64", "r64"):
         for mode in (0, 1):
-            for (U, NT), minbs in BLOCK_MINB.items():
-                for j, minb in enumerate(minbs):
-                    if j > 0 and not (amp == "c128" and mode == 0):
-                        continue      # tuning variants only for the headline type
-                    out.append((f"block_{amp}_m{mode}", amp, U, mode, NT, minb, 0, 1 if j == 0 else 0))
-        # degree-specialised kernels: compat mode, CTA sizes 256 / 128, default occupancy target
+            for (U, SU, NT), minb in BLOCK_MINB.items():
+                if U == 2 and amp != "c128":
+                    continue          # U = 2 is only reachable through the tuning override
+                out.append((f"block_{amp}_m{mode}", amp, U, SU, mode, NT, minb, 0, 1))
+        # degree-specialised kernels: compat mode, CTA sizes 256 / 128
         for dt in range(1, DT_MAX + 1):
-            for (U, NT), minbs in BLOCK_MINB.items():
-                if NT not in (256, 128):
+            for (U, SU, NT), minb in BLOCK_MINB.items():
+                if NT not in (256, 128) or U == 2 or (SU == 2 and dt > SU2_DT_MAX):
                     continue
-                for j, minb in enumerate(minbs):
-                    if j > 0 and not (amp == "c128" and dt in (1, 3)):
-                        continue
-                    out.append((f"block_{amp}_d{dt}", amp, U, 0, NT, minb, dt, 1 if j == 0 else 0))
+                out.append((f"block_{amp}_d{dt}", amp, U, SU, 0, NT, minb, dt, 1))
     return out
 
 
@@ -133,9 +133,9 @@ def main():
         fh.write("// generated by gen_instances.py - do not edit\n")
         fh.write('#include "../qkan_block.cuh"\n#include <vector>\nusing namespace qkan;\n')
         fh.write(f"void qkan_register_{g}(std::vector<BlockKernelInfo>& reg) {{\n")
-        for (_, amp, U, MODE, NT, MINB, DT, dflt) in items:
+        for (_, amp, U, SU, MODE, NT, MINB, DT, dflt) in items:
             A, R, _sz = AMPS[amp]
-            fh.write(f"    reg.push_back(make_block_info<{A}, {R}, {U}, {MODE}, {NT}, {MINB}, {DT}>({dflt}));\n")
+            fh.write(f"    reg.push_back(make_block_info<{A}, {R}, {U}, {SU}, {MODE}, {NT}, {MINB}, {DT}>({dflt}));\n")
         fh.write("}\n")
         wanted.add(f"inst_{g}.cu")
         write_if_changed(os.path.join(d, f"inst_{g}.cu"), fh.getvalue())

@@ -21,6 +21,7 @@
 // (N4 K4 D3: 64 blocks = 256 amplitudes over 16 lanes) is register resident at once.
 #pragma once
 #include "qkan_core.cuh"
+#include <stdlib.h>
 #if defined(__CUDACC__)
 #include "qkan_kernel.cuh"
 #endif
@@ -227,7 +228,7 @@ template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) 
 
 // SIMPLE: every lane owns one whole output row of its sample (G_r = 1 and a single row step - the
 // layout of every small BASELINE layer): no row loop and no shuffle step in the per-sample code.
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool SIMPLE, int DT>
+template <class A, typename R, int U, int SU, int MODE, int NT, int MINB, bool SIMPLE, int DT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int G = p.G, G_r = p.G_r, G_k = p.G_k;
@@ -352,14 +353,21 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         const long long nxt = it + 2 * (long long)gridDim.x;
         if (nxt < n_it) issue_x(nxt, buf);                    // overlaps with the compute of this and the next tile
 
+        // SU samples per lane at a time (the lane's slots of SU consecutive sub-iterations): they share
+        // every table entry, so the loads, pointer bumps and per-sample set-up are paid once per SU samples
         const int nsub = (nsamp + SPC - 1) / SPC;
         const char* csrow = reinterpret_cast<const char*>(cs) + (size_t)slot * NP * sizeof(CS<R>);
         long long o = (p.row0 + s0 + slot) * p.K;
         long long oa = (s0 + slot) * p.K;                     // amps are local: no row offset
         int ls = slot;
-        for (int si = 0; si < nsub; ++si, csrow += row_stride, o += out_stride, oa += out_stride, ls += SPC) {
-            const bool valid = ls < nsamp;
-            const char* row = valid ? csrow : reinterpret_cast<const char*>(cs);   // idle slots of a ragged tile read row 0
+        for (int si = 0; si < nsub; si += SU, csrow += SU * row_stride, o += SU * out_stride, oa += SU * out_stride, ls += SU * SPC) {
+            bool valid[SU];
+            const char* row[SU];
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j) {
+                valid[j] = ls + j * SPC < nsamp;
+                row[j] = valid[j] ? csrow + j * row_stride : reinterpret_cast<const char*>(cs);   // idle slots of a ragged tile read row 0
+            }
             // stream the lane's slots with one running pointer; the next pass's entries are fetched while
             // the current pass is evolved (the tables end with one pass of padding slots)
             const CS<R>* cp = cstab + g;
@@ -368,9 +376,9 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
             int xn[U];
             QK_UNROLL
             for (int u = 0; u < U; ++u) { qn[u] = q0[u]; xn[u] = x0[u]; }
-            auto run_row = [&]() -> A {
-                A acc;
-                set_amp(acc, 0.0);
+            auto run_row = [&](A (&acc)[SU]) {
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) set_amp(acc[j], 0.0);
                 for (int pi = 0; pi < p.passes; ++pi) {
                     QK_UNROLL
                     for (int u = 0; u < U; ++u) unpack(u, qn[u], xn[u]);
@@ -378,40 +386,51 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     xp += (size_t)U * G;
                     QK_UNROLL
                     for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
-                    R cx[U], sx[U];
+                    R cx[SU][U], sx[SU][U];
                     QK_UNROLL
-                    for (int u = 0; u < U; ++u) {
-                        const CS<R> e = *reinterpret_cast<const CS<R>*>(row + xoff[u]);
-                        cx[u] = e.c; sx[u] = e.s;
+                    for (int j = 0; j < SU; ++j) {
+                        QK_UNROLL
+                        for (int u = 0; u < U; ++u) {
+                            const CS<R> e = *reinterpret_cast<const CS<R>*>(row[j] + xoff[u]);
+                            cx[j][u] = e.c; sx[j][u] = e.s;
+                        }
                     }
-                    const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx, sx, cw, sw, deg, p.D);
-                    add_amp(acc, part);
+                    QK_UNROLL
+                    for (int j = 0; j < SU; ++j) {
+                        const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx[j], sx[j], cw, sw, deg, p.D);
+                        add_amp(acc[j], part);
+                    }
                 }
-                return acc;
             };
-            auto write_row = [&](const A& acc, int b) {
+            auto write_row = [&](const A& acc, int b, int j) {
                 const double val = (double)acc.re * p.out_scale;
-                store_result(p, o + b, val);
+                store_result(p, o + j * out_stride + b, val);
                 if (p.amps) {
                     Cplx<R> z;
                     z.re = (R)((double)acc.re * p.amp_scale);
                     if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
                     else z.im = R(0);
-                    reinterpret_cast<Cplx<R>*>(p.amps)[oa + b] = z;
+                    reinterpret_cast<Cplx<R>*>(p.amps)[oa + j * out_stride + b] = z;
                 }
             };
+            A acc[SU];
             if constexpr (SIMPLE) {
                 // every lane owns one whole output row (G_r = 1, one row step): UNPREPARE + SUM +
                 // post-selection is the lane's running sum, no cross-lane step
-                const A acc = run_row();
-                if (valid && k < p.K) write_row(acc, k);
+                run_row(acc);
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j)
+                    if (valid[j] && k < p.K) write_row(acc[j], k, j);
             } else {
                 for (int b = k; b < p.brows * G_k; b += G_k) {
-                    A acc = run_row();
+                    run_row(acc);
                     // UNPREPARE (H on deg) + SUM (H on a) + post-selection deg = a = 0: the sum over the
                     // row's blocks, finished across the G_r lanes with an xor butterfly
-                    for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
-                    if (valid && r == 0 && b < p.K) write_row(acc, b);
+                    QK_UNROLL
+                    for (int j = 0; j < SU; ++j) {
+                        for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[j], shfl_xor_amp(acc[j], m));
+                        if (valid[j] && r == 0 && b < p.K) write_row(acc[j], b, j);
+                    }
                 }
             }
         }
@@ -435,14 +454,15 @@ __global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, 
 
 struct BlockKernelInfo {
     int amp, mode, U, NT, MINB;
+    int SU;                     // samples per lane at a time
     int DT;                     // 0 = any D (run-time loop), else only for D == DT
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
 
-template <class A, typename R, int U, int MODE, int NT, int MINB, bool SIMPLE, int DT>
+template <class A, typename R, int U, int SU, int MODE, int NT, int MINB, bool SIMPLE, int DT>
 cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    auto kern = qkan_block_kernel<A, R, U, MODE, NT, MINB, SIMPLE, DT>;
+    auto kern = qkan_block_kernel<A, R, U, SU, MODE, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
@@ -455,6 +475,7 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
         return xs + cs + 16;
     };
     int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile
+    if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
     if (sub < 1) sub = 1;
     if (smem_for(sub) > 200 * 1024) return cudaErrorInvalidConfiguration;
@@ -480,22 +501,22 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
     return cudaGetLastError();
 }
-template <class A, typename R, int U, int MODE, int NT, int MINB, int DT>
+template <class A, typename R, int U, int SU, int MODE, int NT, int MINB, int DT>
 cudaError_t launch_block(const BlockParams& p, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
     if (DT > 0 && p.D != DT) return cudaErrorInvalidValue;
     if (p.g_r_log2 == 0 && p.brows == 1)
-        return launch_block_impl<A, R, U, MODE, NT, MINB, true, DT>(p, G, sm_count, stream, grid_out, smem_out);
-    return launch_block_impl<A, R, U, MODE, NT, MINB, false, DT>(p, G, sm_count, stream, grid_out, smem_out);
+        return launch_block_impl<A, R, U, SU, MODE, NT, MINB, true, DT>(p, G, sm_count, stream, grid_out, smem_out);
+    return launch_block_impl<A, R, U, SU, MODE, NT, MINB, false, DT>(p, G, sm_count, stream, grid_out, smem_out);
 }
 
 template <class A> struct AmpId;
 
-template <class A, typename R, int U, int MODE, int NT, int MINB, int DT>
+template <class A, typename R, int U, int SU, int MODE, int NT, int MINB, int DT>
 BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
-    k.mode = MODE; k.U = U; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.launch = &launch_block<A, R, U, MODE, NT, MINB, DT>;
+    k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
+    k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
     return k;
 }
 #endif  // __CUDACC__

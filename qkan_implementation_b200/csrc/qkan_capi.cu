@@ -95,11 +95,15 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // block engine: any N, K, D.  Pick the lane layout and the CTA size whose x tile fits.
         if ((long long)N * K >= (1 << 20) || max_degree >= 2048 || (mode == QKAN_MODE_PAPER && max_degree >= 128))
             return fail(QKAN_ERR_UNSUPPORTED, "block engine limits: N*K < 2^20, D < 2048 (D < 128 in paper mode)");
-        const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB" (0 = any)
-        int fU = 0, fNT = 0, fMINB = 0;
-        if (tune) sscanf(tune, "%d:%d:%d", &fU, &fNT, &fMINB);
+        const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB:SU" (0 = any)
+        int fU = 0, fNT = 0, fMINB = 0, fSU = 0;
+        if (tune) sscanf(tune, "%d:%d:%d:%d", &fU, &fNT, &fMINB, &fSU);
+        // two samples per lane share every table entry: measured +4..+15 % for D <= 4 (fixed per-block overhead
+        // matters there), slower for deep sequences (profiles/r01_tune_block_engine_v12_su2.jsonl)
+        const int want_SU = fSU ? fSU : (max_degree <= 4 ? 2 : 1);
         const size_t per_x = 2 * amp_real_size(dtype);           // the (cos, sin) pair (wide rows skip the raw-x staging)
-        const int NTs[4] = {256, 128, 64, 32};
+        const int NTs_a[4] = {256, 128, 64, 32}, NTs_b[4] = {128, 256, 64, 32};
+        const int* NTs = (want_SU == 2) ? NTs_b : NTs_a;
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
             const int NT = NTs[ni];
             if (fNT && NT != fNT) continue;
@@ -119,6 +123,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
                     if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
+                    if (k.SU != ((cand.U == 1 && (NT == 256 || NT == 128)) ? want_SU : 1)) continue;
                     if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
                     if (k.DT == max_degree && !getenv("QKAN_BLOCK_NO_DT")) { bbest = &k; break; }   // degree-specialised
                     if (k.DT == 0 && !generic) generic = &k;
@@ -417,6 +422,7 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         const int G = 1 << (l->lay.g_r_log2 + l->lay.g_k_log2);
         info->blocks = l->N * l->K * (l->D + 1);
         info->unroll = k.U;
+        info->samples_per_lane = k.SU;
         info->lanes_per_sample = G;
         info->lanes_per_row = 1 << l->lay.g_r_log2;
         info->rows_in_parallel = 1 << l->lay.g_k_log2;

@@ -19,7 +19,8 @@ CONFIGS = {"c2": (4, 4, 3, 1_000_000), "c5d1": (8, 8, 1, 1_000_000), "c5d2": (8,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c5d1,c5d4,c5d16,c3")
-    ap.add_argument("--variants", default="0:0:0,4:256:2,4:256:1,4:128:4,4:128:3,4:128:2,2:256:3,2:256:2,2:256:4,2:128:6,2:128:4,2:128:8,1:256:4,1:256:3,1:256:6,1:128:8,1:128:6,1:128:12")
+    ap.add_argument("--variants", default="0:0:0:0,1:256:4:1,1:128:8:1,1:256:3:2,1:128:6:2,2:256:3:1,4:256:2:1,4:128:4:1",
+                    help="QKAN_BLOCK_TUNE values U:NT:MINB:SU (0 = planner default); only built combinations resolve")
     ap.add_argument("--dtype", default="complex128")
     ap.add_argument("--prep", default="analytic")
     a = ap.parse_args()
@@ -41,7 +42,7 @@ def main():
                 print(name, "variant", v, "failed:", e)
                 continue
             info = layer.kernel_info()
-            key = (info["unroll"], info["lanes_per_sample"], info["tile_qubits"], info["local_qubits"], info["threads_per_cta"], info["min_ctas_per_sm"], info["grid"], info["smem_bytes"])
+            key = (info["unroll"], info["samples_per_lane"], info["lanes_per_sample"], info["tile_qubits"], info["local_qubits"], info["threads_per_cta"], info["min_ctas_per_sm"], info["grid"], info["smem_bytes"])
             if key in seen:
                 continue
             seen.add(key)
@@ -60,7 +61,7 @@ def main():
                 ts.append(ev0.elapsed_time(ev1))
             ms = float(np.median(ts))
             tf = info["flops_exec"] * B / (ms * 1e-3) / 1e12
-            print(json.dumps({"cfg": name, "variant": v, "U": info["unroll"], "G": info["lanes_per_sample"], "NT": info["threads_per_cta"],
+            print(json.dumps({"cfg": name, "variant": v, "U": info["unroll"], "SU": info["samples_per_lane"], "G": info["lanes_per_sample"], "NT": info["threads_per_cta"],
                               "MINB": info["min_ctas_per_sm"], "passes": info["passes"], "rows": info["row_steps"],
                               "tileq": info["tile_qubits"], "T": info["local_qubits"], "grid": info["grid"],
                               "cta_per_sm": round(info["grid"] / 148, 2), "smem": info["smem_bytes"], "ms": round(ms, 4),

@@ -16,6 +16,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def ensure_library_built():
+    """The CUDA library is a build artefact (git-ignored): build it once if the tree is fresh.
+    nvcc cross-compiles sm_100a without a GPU (about a minute on 8 cores)."""
+    lib = os.path.join(ROOT, "qkan_implementation_b200", "libqkan_b200.so")
+    if not os.path.exists(lib):
+        import __graft_entry__ as g
+        g.build()
+
+
 def golden_batches():
     """[(N, K, D, path)] of the fixtures written by oracle/gen_golden.py from the unmodified reference."""
     out = []

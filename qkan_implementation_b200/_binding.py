@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqkan_b200.so")
+LIB_PATH = os.environ.get("QKAN_B200_LIB", os.path.join(_HERE, "libqkan_b200.so"))   # override = tuning aid
 
 QKAN_OK = 0
 ERR_BAD_SHAPE, ERR_UNSUPPORTED, ERR_WEIGHT_RANGE, ERR_CUDA, ERR_NO_WEIGHTS = -1, -2, -3, -4, -5

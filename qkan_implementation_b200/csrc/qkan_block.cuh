@@ -215,7 +215,9 @@ __device__ __forceinline__ void store_result(const BlockParams& p, long long idx
     if (p.mc_out != nullptr) {
         asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p.mc_out + idx), "d"(val) : "memory");
     } else {
-        for (int q = 0; q < p.n_out; ++q) p.outs[q][idx] = val;
+        p.outs[0][idx] = val;
+#pragma unroll 1
+        for (int q = 1; q < p.n_out; ++q) p.outs[q][idx] = val;     // NVLink peers (fused gather)
     }
 }
 

@@ -36,6 +36,18 @@ struct BlockLayout {
     double efficiency;          // live block slots / issued block slots
 };
 
+// cs row stride (entries).  One LDS phase serves 128 bytes = P lanes (P = 8 for 16-byte pairs, 16 for 8-byte
+// pairs); with G < P lanes per sample a phase spans P / G consecutive sample rows, and the lanes of a row read
+// G different entries, so the rows must start G entries apart modulo P: stride = G (mod P).  Only worth
+// it for narrow rows (N + 1 <= 2 P); wider rows keep N + 1.
+inline int cs_row_stride(int N, int G, int pair_bytes) {
+    const int P = 128 / pair_bytes;
+    int np = N + 1;
+    if (G < P && np <= 2 * P)
+        while (np % P != G % P) ++np;
+    return np;
+}
+
 // pick (U, G_r, G_k): maximise slot efficiency, then prefer one block per lane at a time (fewest
 // registers -> most warps; measured best or equal on every BASELINE config, profiles/r01_tune_*),
 // fewer shuffle steps, more rows in parallel.
@@ -93,6 +105,8 @@ struct BlockParams {
     // not spend registers or instructions on them)
     int G, G_r, G_k;            // lanes per sample / per row / rows in parallel
     int SPC, tile;              // samples in flight per CTA; samples per x tile (SPC * sub)
+    int NP;                     // cs row stride in entries: >= N + 1, padded so that the lanes of one shared-memory
+                                // phase (128 bytes) hit different banks (see cs_row_stride)
     int pre_log2;               // pre-pass: 2^pre_log2 threads share one input row (>= min(N, 32), no division)
     double out_scale, amp_scale;
     double init[8];             // prepared block state, 4 complex amplitudes (re, im): (1,0,0,0) un-normalised
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int G = p.G, G_r = p.G_r, G_k = p.G_k;
     const int SPC = p.SPC;                                   // samples in flight per CTA
     const int tile = p.tile;                                 // samples per x tile
-    const int NP = p.N + 1;                                  // cs row: N rotation pairs + the dummy (0, 1)
+    const int NP = p.NP;                                     // cs row stride: N rotation pairs + the dummy (0, 1) (+ padding)
     // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (clip + sqrt of the current tile) | mbar[2]
     const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
     double* xs0 = reinterpret_cast<double*>(smem_raw);
@@ -467,16 +481,19 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     auto kern = qkan_block_kernel<A, R, U, SU, MODE, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
+    p.NP = cs_row_stride(p.N, G, (int)sizeof(CS<R>));
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
     // halve the resident warps; the per-tile compute is long, so the pre-pass reads global memory directly
     p.direct_x = ((size_t)SPC * p.N * 16 > 16 * 1024) ? 1 : 0;
     auto smem_for = [&](int sub) {
         const size_t tile = (size_t)SPC * sub;
         const size_t xs = p.direct_x ? 0 : 2 * ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
-        const size_t cs = (tile * (p.N + 1) * sizeof(CS<R>) + 15) & ~(size_t)15;
+        const size_t cs = (tile * (size_t)p.NP * sizeof(CS<R>) + 15) & ~(size_t)15;
         return xs + cs + 16;
     };
-    int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile
+    int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile ...
+    const int sub_cs = (int)(24576 / ((size_t)SPC * p.NP * sizeof(CS<R>)));   // ... and at most 24 KiB of rotation pairs
+    if (sub > sub_cs) sub = sub_cs;
     if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
     if (sub < 1) sub = 1;

@@ -15,12 +15,25 @@ MAX_SMEM = 200 * 1024     # leave room for x tiles / accumulators under the 227 
 def shape(amp, L, NAT, NBT, T=None, NT=None, MINB=1):
     """pick T / NT for a tile; returns None if it cannot fit one CTA"""
     QT = L + 2 + NAT + NBT
+    if T is None and NT is None:
+        # measured on B200 (profiles/r01_tune_variants_2.jsonl): small tiles want few registers and many
+        # CTAs, 12-13 qubit tiles want 32 amplitudes per thread
+        if QT <= 9:
+            T, NT, MINB = min(3, QT), 256, 3
+        elif QT <= 11:
+            T, NT, MINB = 4, 128, 4
+        elif QT == 12:
+            T, NT, MINB = 5, 128, 2
+        else:
+            T, NT, MINB = 5, 256, 1
     if T is None:
         T = min(4, QT)
     T = max(2, min(T, QT))
     G = 1 << (QT - T)
     if NT is None:
         NT = max(256, G)
+    if G > NT:
+        NT = G
     if G > 1024 or NT > 1024 or G > NT:
         return None
     if NT * MINB > 2048 or 65536 // (NT * MINB) < 40:

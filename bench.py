@@ -102,7 +102,19 @@ def cpu_reference_rate(a, x, W, per_worker=0, workers=None):
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
+    # context: the gate-level NumPy statevector simulation of the same circuit (the closest thing here to the
+    # north-star's "Qiskit Statevector on CPU", which cannot be installed), one thread, small batch
+    sv_rate = None
+    try:
+        if (1 << o.circuit_spec(N, K, D).qubits) <= (1 << 14):
+            nb = 256 if (1 << o.circuit_spec(N, K, D).qubits) <= 4096 else 16
+            t0 = time.perf_counter()
+            o.statevector_forward(x[:nb], W, N, K, D)
+            sv_rate = nb / (time.perf_counter() - t0)
+    except Exception:      # noqa: BLE001
+        sv_rate = None
     return {"value": total / busy, "unit": "samples/s", "cores": cores, "kind": "port", "wall_s": wall,
+            "numpy_statevector_1thread_samples_per_s": sv_rate,
             "sample": f"{total} samples ({per_worker}/worker) of the same workload through oracle.forward_reference_style "
                       f"(dense np.diag algebra per sample, like QKANLayer.py:122-135); single-thread {1.0 / one:.1f} samples/s; "
                       f"pool wall {wall:.1f}s"}

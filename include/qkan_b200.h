@@ -108,6 +108,9 @@ typedef struct {
     int grid, smem_bytes;       /* of the most recent launch (0 before the first)                         */
     /* work per sample */
     int passes_survey, passes_exec;
+    int scaled_rotations;       /* 1: CHEB passes run in the scaled form Ry = gamma * M(t), one FMA per real output,
+                                   gamma^D and the quarter turns deferred to the last pass (block engine, compat
+                                   mode, 2 <= D <= 16); 0: plain (cos, sin) rotations                         */
     double flops_survey;        /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)                     */
     double flops_exec;          /* arithmetic the kernel executes (DFMA = 2, DMUL = DADD = 1)             */
     double fp_inst_exec;        /* FP64 (FP32 for complex64) lane-instructions behind flops_exec          */

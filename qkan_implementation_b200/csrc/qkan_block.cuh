@@ -37,14 +37,17 @@ struct BlockLayout {
 };
 
 // cs row stride (entries).  One LDS phase serves 128 bytes = P lanes (P = 8 for 16-byte pairs, 16 for 8-byte
-// pairs); with G < P lanes per sample a phase spans P / G consecutive sample rows, and the lanes of a row read
-// G different entries, so the rows must start G entries apart modulo P: stride = G (mod P).  Only worth
-// it for narrow rows (N + 1 <= 2 P); wider rows keep N + 1.
-inline int cs_row_stride(int N, int G, int pair_bytes) {
-    const int P = 128 / pair_bytes;
+// words, 32 for 4-byte words); with G < P lanes per sample a phase spans P / G consecutive sample rows, and
+// the lanes of a row read G different entries, so the rows must start G entries apart modulo P:
+// row stride = mult * NP = G (mod P), where mult = entries-worth of words per row entry (1 for the
+// (cos, sin) pair rows, 3 for the three word rows t | alpha | beta of the scaled-rotation form; 3 is
+// coprime to P, so a solution exists within P steps).  Only worth it for narrow rows (N + 1 <= 2 P);
+// wider rows keep N + 1.
+inline int cs_row_stride(int N, int G, int word_bytes, int mult = 1) {
+    const int P = 128 / word_bytes;
     int np = N + 1;
     if (G < P && np <= 2 * P)
-        while (np % P != G % P) ++np;
+        while ((mult * np) % P != G % P) ++np;
     return np;
 }
 
@@ -122,7 +125,7 @@ struct BlockParams {
 // rotate by theta = pi (c = 0) and read the row's dummy (0, 1) entry: they add exactly 0.
 template <typename R>
 QK_HD void fill_block_slot(long long slot, const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
-                           int g_k_log2, int paper, CS<R>* cstab, int* xotab) {
+                           int g_k_log2, int paper, CS<R>* cstab, int* xotab, int x_entry_bytes = (int)sizeof(CS<R>)) {
     const int g_log2 = g_r_log2 + g_k_log2;
     const int g = (int)(slot & ((1ll << g_log2) - 1));
     long long t = slot >> g_log2;
@@ -134,14 +137,14 @@ QK_HD void fill_block_slot(long long slot, const double* W, int N, int K, int D,
     const long long i = ((long long)(pi << g_r_log2) + r) * U + u;
     CS<R> q;
     q.c = R(0); q.s = R(1);
-    int xo = N * (int)sizeof(CS<R>);                    // dummy (0, 1) entry at the end of every cs row
+    int xo = N * x_entry_bytes;                         // dummy entry (x = 0) at the end of every cs row
     if (b < K && i < (long long)N * (D + 1)) {
         const int a = (int)(i / (D + 1)), d = (int)(i - (long long)a * (D + 1));
         const int flat = a + N * b;
         const R w = (R)W[(long long)d * N * K + flat];
         q.c = w;
         q.s = qk_sqrt((R(1) - w) * (R(1) + w));
-        xo = (flat / K) * (int)sizeof(CS<R>);
+        xo = (flat / K) * x_entry_bytes;
         if (paper) xo |= d << 24;
     }
     cstab[slot] = q;
@@ -223,6 +226,113 @@ QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], co
     return acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Scaled-rotation form of the CHEB sequence (compat mode, compile-time degree DT >= 2).
+//
+// Ry(theta_x) = [[c, -s], [s, c]] is a scalar times a matrix with a unit diagonal:
+//     |c| >= s :  Ry = c * M(t),       t =  s / c,    M(t) = [[1, -t], [t, 1]]
+//     |c| <  s :  Ry = s * J * M(t),   t = -c / s,    J = Ry(pi) = [[0, -1], [1, 0]]   (|t| <= 1 either way)
+// M(t) costs one FMA per real output (u - t v, v + t u) where the (c, s) form needs a multiply and an
+// FMA, so a full CHEB pass over a block is 8 FP64 instructions instead of 16.  Rotations about one
+// axis commute, hence Ry^D = gamma^D * J^D * M(t)^D: the scalar gamma^D (gamma = c or s) and the
+// quarter turns J^D (a signed swap fixed by D mod 4) are deferred to the last, pruned pass, which
+// evaluates the f_x = 0 output of gamma^D J^D M(t) as alpha u + beta v.  This is the same device as
+// folding the 1/sqrt(2) of every Hadamard into the read-out scale; every amplitude of every block
+// is still evolved through every gate.  |t| <= 1 bounds the un-normalised state by 2^(D/2), which
+// is why the form is used for the degree-specialised kernels (D <= 16) only.
+#ifndef QKAN_TAN_FORM
+#define QKAN_TAN_FORM 1
+#endif
+constexpr int TAN_MIN_DT = 2;        // D = 1 has no full pass to save; its pre-pass would only get dearer
+// U = 1 only: the U = 4 kernels serve wide input rows, where the cs tile (24 instead of 16 bytes per input
+// element) already limits the resident warps (measured on N784 K10 D5: 3.97 -> 2.96 M samples/s with triples)
+constexpr bool use_tan_form(int mode, int dt, int U) { return QKAN_TAN_FORM && mode == 0 && dt >= TAN_MIN_DT && U == 1; }
+
+template <typename R> struct TanEntry { R t, al, be; };
+
+// per input element, once per sample (pre-pass): c = clipped x
+template <typename R> QK_HD TanEntry<R> tan_entry(R c, int D) {
+    const R s = qk_sqrt((R(1) - c) * (R(1) + c));
+    const bool quarter = (c < R(0) ? -c : c) < s;
+    const R gam = quarter ? s : c;
+    const R inv = R(1) / gam;
+    const R t = quarter ? -(c * inv) : s * inv;
+    R g = gam;
+    for (int i = 1; i < D; ++i) g *= gam;
+    const R gt = g * t;
+    TanEntry<R> e;
+    e.t = t;
+    // f_x = 0 output of g J^D (u - t v, v + t u)
+    switch (quarter ? (D & 3) : 0) {
+        case 0: e.al = g; e.be = -gt; break;
+        case 1: e.al = -gt; e.be = -g; break;
+        case 2: e.al = -g; e.be = gt; break;
+        default: e.al = gt; e.be = g; break;
+    }
+    return e;
+}
+
+// (u, v) <- (u - t v, v + t u): one FMA per real output
+template <typename R> QK_HD void rot_tan(Cplx<R>& u, Cplx<R>& v, R t) {
+    const R ur = u.re, ui = u.im;
+    u.re = qk_fma(-t, v.re, ur);
+    u.im = qk_fma(-t, v.im, ui);
+    v.re = qk_fma(t, ur, v.re);
+    v.im = qk_fma(t, ui, v.im);
+}
+template <typename R> QK_HD void rot_tan(Real<R>& u, Real<R>& v, R t) {
+    const R ur = u.re;
+    u.re = qk_fma(-t, v.re, ur);
+    v.re = qk_fma(t, ur, v.re);
+}
+template <typename R> QK_HD Cplx<R> lin2(const Cplx<R>& u, const Cplx<R>& v, R a, R b) {
+    Cplx<R> o;
+    o.re = qk_fma(a, u.re, b * v.re);
+    o.im = qk_fma(a, u.im, b * v.im);
+    return o;
+}
+template <typename R> QK_HD Real<R> lin2(const Real<R>& u, const Real<R>& v, R a, R b) {
+    Real<R> o;
+    o.re = qk_fma(a, u.re, b * v.re);
+    return o;
+}
+template <typename R> QK_HD void fma_amp(Cplx<R>& acc, R c, const Cplx<R>& z) {
+    acc.re = qk_fma(c, z.re, acc.re);
+    acc.im = qk_fma(c, z.im, acc.im);
+}
+template <typename R> QK_HD void fma_amp(Real<R>& acc, R c, const Real<R>& z) { acc.re = qk_fma(c, z.re, acc.re); }
+
+// Same contract as evolve_blocks, accumulating into acc:
+//   CHEB applications 1 .. DT-1: full scaled passes on both f_w halves              8 instr / 16 flops
+//   CHEB application DT (pruned to f_x = 0, with gamma^D J^D):  alpha u + beta v    8 instr / 12 flops
+//   MUL (pruned to (0,0)) fused with the read-out sum: acc += cw lo0 - sw lo2       4 instr /  8 flops
+// (complex amplitudes; half of that for the real-only representation)
+template <class A, typename R, int U, int DT>
+QK_HD void evolve_blocks_tan(const A (&init)[4], const R (&t)[U], const R (&al)[U], const R (&be)[U], const R (&cw)[U],
+                             const R (&sw)[U], A& acc) {
+    A v[U][4];
+    QK_UNROLL
+    for (int u = 0; u < U; ++u) {
+        QK_UNROLL
+        for (int q = 0; q < 4; ++q) v[u][q] = init[q];
+    }
+    QK_UNROLL
+    for (int r = 0; r + 1 < DT; ++r) {
+        QK_UNROLL
+        for (int u = 0; u < U; ++u) {
+            rot_tan(v[u][0], v[u][1], t[u]);
+            rot_tan(v[u][2], v[u][3], t[u]);
+        }
+    }
+    QK_UNROLL
+    for (int u = 0; u < U; ++u) {
+        const A lo0 = lin2(v[u][0], v[u][1], al[u], be[u]);
+        const A lo2 = lin2(v[u][2], v[u][3], al[u], be[u]);
+        fma_amp(acc, cw[u], lo0);
+        fma_amp(acc, -sw[u], lo2);
+    }
+}
+
 #if defined(__CUDACC__)
 // result store: to every listed buffer (local + NVLink peers), or once through the multicast mapping
 __device__ __forceinline__ void store_result(const BlockParams& p, long long idx, double val) {
@@ -250,13 +360,18 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int G = p.G, G_r = p.G_r, G_k = p.G_k;
     const int SPC = p.SPC;                                   // samples in flight per CTA
     const int tile = p.tile;                                 // samples per x tile
-    const int NP = p.NP;                                     // cs row stride: N rotation pairs + the dummy (0, 1) (+ padding)
-    // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (clip + sqrt of the current tile) | mbar[2]
+    const int NP = p.NP;                                     // cs row stride: N entries + the dummy (+ padding)
+    // scaled-rotation form: a sample's cs row is three word rows t[NP] | alpha[NP] | beta[NP] instead of NP (cos, sin) pairs
+    constexpr bool TAN = use_tan_form(MODE, DT, U);
+    constexpr size_t ROWB = TAN ? 3 * sizeof(R) : sizeof(CS<R>);   // cs bytes per entry of a row
+    // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (rotation entries of the current tile) | mbar[2]
     const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
     double* xs0 = reinterpret_cast<double*>(smem_raw);
     CS<R>* cs = reinterpret_cast<CS<R>*>(smem_raw + 2 * xs_doubles * sizeof(double));
+    R* csw = reinterpret_cast<R*>(cs);
+    const size_t npb = (size_t)NP * sizeof(R);               // TAN: bytes between the t / alpha / beta word rows
     unsigned long long* mbar =
-        reinterpret_cast<unsigned long long*>(smem_raw + 2 * xs_doubles * sizeof(double) + (((size_t)tile * NP * sizeof(CS<R>) + 15) & ~(size_t)15));
+        reinterpret_cast<unsigned long long*>(smem_raw + 2 * xs_doubles * sizeof(double) + (((size_t)tile * NP * ROWB + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x;
     const int g = tid & (G - 1);
@@ -274,9 +389,15 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     }
     // the dummy entries never change
     for (int i = tid; i < tile; i += NT) {
-        CS<R> e;
-        e.c = R(0); e.s = R(1);
-        cs[(size_t)i * NP + p.N] = e;
+        if constexpr (TAN) {
+            const TanEntry<R> e = tan_entry<R>(R(0), DT);
+            R* cr = csw + (size_t)i * 3 * NP;
+            cr[p.N] = e.t; cr[NP + p.N] = e.al; cr[2 * NP + p.N] = e.be;
+        } else {
+            CS<R> e;
+            e.c = R(0); e.s = R(1);
+            cs[(size_t)i * NP + p.N] = e;
+        }
     }
     __syncthreads();
 
@@ -331,7 +452,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     if (it + gridDim.x < n_it) issue_x(it + gridDim.x, 1);
     __syncthreads();
 
-    const size_t row_stride = (size_t)SPC * NP * sizeof(CS<R>);   // bytes between consecutive sub-iterations
+    const size_t row_stride = (size_t)SPC * NP * ROWB;            // bytes between consecutive sub-iterations
     const long long out_stride = (long long)SPC * p.K;
 
     for (; it < n_it; it += gridDim.x, buf ^= 1) {
@@ -353,14 +474,20 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
             for (int row = tid >> p.pre_log2; row < nsamp; row += NT >> p.pre_log2) {
                 const double* xr = xs + (size_t)row * p.N;
                 CS<R>* cr = cs + (size_t)row * NP;
+                R* crw = csw + (size_t)row * 3 * NP;
                 for (int n = n0; n < p.N; n += gs) {
                     const double v = xr[n];
                     if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
                     const R c = clip_unit<R>(v);
-                    CS<R> e;
-                    e.c = c;
-                    e.s = qk_sqrt((R(1) - c) * (R(1) + c));
-                    cr[n] = e;
+                    if constexpr (TAN) {
+                        const TanEntry<R> e = tan_entry<R>(c, DT);
+                        crw[n] = e.t; crw[NP + n] = e.al; crw[2 * NP + n] = e.be;
+                    } else {
+                        CS<R> e;
+                        e.c = c;
+                        e.s = qk_sqrt((R(1) - c) * (R(1) + c));
+                        cr[n] = e;
+                    }
                 }
             }
         }
@@ -372,7 +499,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         // SU samples per lane at a time (the lane's slots of SU consecutive sub-iterations): they share
         // every table entry, so the loads, pointer bumps and per-sample set-up are paid once per SU samples
         const int nsub = (nsamp + SPC - 1) / SPC;
-        const char* csrow = reinterpret_cast<const char*>(cs) + (size_t)slot * NP * sizeof(CS<R>);
+        const char* csrow = reinterpret_cast<const char*>(cs) + (size_t)slot * NP * ROWB;
         long long o = (p.row0 + s0 + slot) * p.K;
         long long oa = (s0 + slot) * p.K;                     // amps are local: no row offset
         int ls = slot;
@@ -402,19 +529,35 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     xp += (size_t)U * G;
                     QK_UNROLL
                     for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
-                    R cx[SU][U], sx[SU][U];
-                    QK_UNROLL
-                    for (int j = 0; j < SU; ++j) {
+                    if constexpr (TAN) {
+                        R tx[SU][U], ax[SU][U], bx[SU][U];
                         QK_UNROLL
-                        for (int u = 0; u < U; ++u) {
-                            const CS<R> e = *reinterpret_cast<const CS<R>*>(row[j] + xoff[u]);
-                            cx[j][u] = e.c; sx[j][u] = e.s;
+                        for (int j = 0; j < SU; ++j) {
+                            QK_UNROLL
+                            for (int u = 0; u < U; ++u) {
+                                const char* e = row[j] + xoff[u];
+                                tx[j][u] = *reinterpret_cast<const R*>(e);
+                                ax[j][u] = *reinterpret_cast<const R*>(e + npb);
+                                bx[j][u] = *reinterpret_cast<const R*>(e + 2 * npb);
+                            }
                         }
-                    }
-                    QK_UNROLL
-                    for (int j = 0; j < SU; ++j) {
-                        const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx[j], sx[j], cw, sw, deg, p.D);
-                        add_amp(acc[j], part);
+                        QK_UNROLL
+                        for (int j = 0; j < SU; ++j) evolve_blocks_tan<A, R, U, DT>(init, tx[j], ax[j], bx[j], cw, sw, acc[j]);
+                    } else {
+                        R cx[SU][U], sx[SU][U];
+                        QK_UNROLL
+                        for (int j = 0; j < SU; ++j) {
+                            QK_UNROLL
+                            for (int u = 0; u < U; ++u) {
+                                const CS<R> e = *reinterpret_cast<const CS<R>*>(row[j] + xoff[u]);
+                                cx[j][u] = e.c; sx[j][u] = e.s;
+                            }
+                        }
+                        QK_UNROLL
+                        for (int j = 0; j < SU; ++j) {
+                            const A part = evolve_blocks<A, R, U, MODE, DT>(init, cx[j], sx[j], cw, sw, deg, p.D);
+                            add_amp(acc[j], part);
+                        }
                     }
                 }
             };
@@ -456,11 +599,11 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 
 template <typename R>
 __global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
-                                                 int g_k_log2, int paper, long long slots_total, CS<R>* cstab, int* xotab,
-                                                 unsigned long long* bad_weights) {
+                                                 int g_k_log2, int paper, int x_entry_bytes, long long slots_total,
+                                                 CS<R>* cstab, int* xotab, unsigned long long* bad_weights) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= slots_total) return;
-    fill_block_slot<R>(slot, W, N, K, D, U, passes, g_r_log2, g_k_log2, paper, cstab, xotab);
+    fill_block_slot<R>(slot, W, N, K, D, U, passes, g_r_log2, g_k_log2, paper, cstab, xotab, x_entry_bytes);
     // |w| <= 1 is required for the rotation to exist (MulStep.py:36-37): check each weight once
     if (slot < (long long)N * K * (D + 1)) {
         const double w = W[slot];
@@ -472,6 +615,7 @@ struct BlockKernelInfo {
     int amp, mode, U, NT, MINB;
     int SU;                     // samples per lane at a time
     int DT;                     // 0 = any D (run-time loop), else only for D == DT
+    int tan;                    // scaled-rotation form (use_tan_form): cs rows are t | alpha | beta word rows
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
@@ -481,18 +625,20 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     auto kern = qkan_block_kernel<A, R, U, SU, MODE, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
-    p.NP = cs_row_stride(p.N, G, (int)sizeof(CS<R>));
+    constexpr bool TAN = use_tan_form(MODE, DT, U);
+    constexpr size_t ROWB = TAN ? 3 * sizeof(R) : sizeof(CS<R>);
+    p.NP = TAN ? cs_row_stride(p.N, G, (int)sizeof(R), 3) : cs_row_stride(p.N, G, (int)sizeof(CS<R>));
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
     // halve the resident warps; the per-tile compute is long, so the pre-pass reads global memory directly
     p.direct_x = ((size_t)SPC * p.N * 16 > 16 * 1024) ? 1 : 0;
     auto smem_for = [&](int sub) {
         const size_t tile = (size_t)SPC * sub;
         const size_t xs = p.direct_x ? 0 : 2 * ((tile * p.N + 1) & ~(size_t)1) * sizeof(double);
-        const size_t cs = (tile * (size_t)p.NP * sizeof(CS<R>) + 15) & ~(size_t)15;
+        const size_t cs = (tile * (size_t)p.NP * ROWB + 15) & ~(size_t)15;
         return xs + cs + 16;
     };
     int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile ...
-    const int sub_cs = (int)(24576 / ((size_t)SPC * p.NP * sizeof(CS<R>)));   // ... and at most 24 KiB of rotation pairs
+    const int sub_cs = (int)((TAN ? 36864 : 24576) / ((size_t)SPC * p.NP * ROWB));   // ... and at most 24 KiB of rotation pairs (36 KiB of triples)
     if (sub > sub_cs) sub = sub_cs;
     if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
@@ -535,6 +681,7 @@ BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
+    k.tan = use_tan_form(MODE, DT, U) ? 1 : 0;
     k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
     return k;
 }

@@ -101,7 +101,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // two samples per lane share every table entry: measured +4..+15 % for D <= 4 (fixed per-block overhead
         // matters there), slower for deep sequences (profiles/r01_tune_block_engine_v12_su2.jsonl)
         const int want_SU = fSU ? fSU : (max_degree <= 4 ? 2 : 1);
-        const size_t per_x = 2 * amp_real_size(dtype);           // the (cos, sin) pair (wide rows skip the raw-x staging)
+        // the (cos, sin) pair, or the (t, alpha, beta) triple of the scaled-rotation kernels (wide rows skip the raw-x staging)
+        const bool tan_dt = max_degree <= 16 && !getenv("QKAN_BLOCK_NO_DT");
         const int NTs_a[4] = {256, 128, 64, 32}, NTs_b[4] = {128, 256, 64, 32};
         const int* NTs = (want_SU == 2) ? NTs_b : NTs_a;
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
@@ -111,15 +112,18 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
                 int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                 if (G < (1 << min_g) || G > NT) continue;
-                const size_t cs_bytes = (size_t)(NT / G) * (N + 1) * per_x;
-                if (cs_bytes > 72 * 1024) continue;
+                auto cs_bytes_for = [&](int U) {
+                    const size_t per_x = (use_tan_form(mode, tan_dt ? max_degree : 0, U) ? 3 : 2) * amp_real_size(dtype);
+                    return (size_t)(NT / G) * (N + 1) * per_x;
+                };
                 // wide input rows: shared memory limits the resident warps (< 24 per SM), so keep four blocks
                 // per lane in flight instead of one (measured on N784 K10 D5: 3.7 -> 4.0 M samples/s)
-                if (!fU && (220 * 1024 / (cs_bytes + 1024)) * (size_t)(NT / 32) < 24) {
+                if (!fU && (220 * 1024 / (cs_bytes_for(cand.U) + 1024)) * (size_t)(NT / 32) < 24) {
                     const BlockLayout wide = plan_block_layout(N, K, max_degree, min_g, 4);
                     const int Gw = 1 << (wide.g_r_log2 + wide.g_k_log2);
                     if (Gw == G) cand = wide;
                 }
+                if (cs_bytes_for(cand.U) > 72 * 1024) continue;
                 const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
                     if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
@@ -223,11 +227,13 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
         const unsigned nt = 128, nb = (unsigned)((slots + nt - 1) / nt);
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
-                                                                           l->lay.g_r_log2, l->lay.g_k_log2, l->mode, slots,
+                                                                           l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
+                                                                           l->bkern->tan ? 4 : 8, slots,
                                                                            (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
-                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode, slots,
+                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
+                                                                            l->bkern->tan ? 8 : 16, slots,
                                                                             (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);
@@ -438,6 +444,13 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         const double Dd = (double)l->D;
         info->flops_exec = cf * (double)info->blocks * (l->D > 0 ? 24.0 * Dd - 4.0 : 8.0);
         info->fp_inst_exec = cf * (double)info->blocks * (l->D > 0 ? 16.0 * Dd - 2.0 : 6.0);
+        info->scaled_rotations = k.tan;
+        if (k.tan) {
+            // scaled-rotation form (evolve_blocks_tan): D-1 full passes of 8 FMA, the pruned last pass
+            // alpha u + beta v (4 MUL + 4 FMA), SELECT fused with the read-out sum (4 FMA)
+            info->flops_exec = cf * (double)info->blocks * (16.0 * Dd + 4.0);
+            info->fp_inst_exec = cf * (double)info->blocks * (8.0 * Dd + 4.0);
+        }
         info->layout_efficiency = l->lay.efficiency;
     } else {
         const KernelInfo& k = *l->kern;

@@ -106,8 +106,21 @@ extern "C" int qkan_emu_forward(int cfg, const double* x, const double* W, long 
 }
 
 // ---- block engine: lanes of a group run sequentially, the xor butterfly is replayed on arrays
+template <class A, typename R, int U, int DT> struct TanRun {
+    static void go(int D, const A (&init)[4], const R (&t)[U], const R (&al)[U], const R (&be)[U], const R (&cw)[U],
+                   const R (&sw)[U], A& acc) {
+        if (D == DT) evolve_blocks_tan<A, R, U, DT>(init, t, al, be, cw, sw, acc);
+        else TanRun<A, R, U, DT - 1>::go(D, init, t, al, be, cw, sw, acc);
+    }
+};
+template <class A, typename R, int U> struct TanRun<A, R, U, 1> {
+    static void go(int, const A (&)[4], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], A&) {}
+};
+
+// tan != 0: the scaled-rotation form of the degree-specialised kernels (compat mode, 2 <= D <= 16)
 template <class A, typename R, int U, int MODE>
-int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, double* out, double* amps) {
+int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, int tan, double* out, double* amps) {
+    if (tan && (MODE != 0 || D < TAN_MIN_DT || D > 16)) return -4;
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
     if (lay.U != U) return -3;
     const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
@@ -115,7 +128,9 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
     std::vector<CS<R>> cstab(slots);
     std::vector<int> xotab(slots);
     for (long long e = 0; e < slots; ++e)
-        fill_block_slot<R>(e, W, N, K, D, U, lay.passes, lay.g_r_log2, lay.g_k_log2, MODE, cstab.data(), xotab.data());
+        fill_block_slot<R>(e, W, N, K, D, U, lay.passes, lay.g_r_log2, lay.g_k_log2, MODE, cstab.data(), xotab.data(),
+                           tan ? (int)sizeof(R) : (int)sizeof(CS<R>));
+    const int NP = tan ? cs_row_stride(N, G, (int)sizeof(R), 3) : N + 1;
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
     while ((1 << NB) < K) ++NB;
@@ -125,6 +140,12 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
         std::vector<CS<R>> cs(N + 1);
         for (int n = 0; n < N; ++n) { R c = clip_unit<R>(x[s * N + n]); cs[n].c = c; cs[n].s = qk_sqrt((R(1) - c) * (R(1) + c)); }
         cs[N].c = 0; cs[N].s = 1;
+        std::vector<R> csw(3 * (size_t)NP, R(0));            // t | alpha | beta word rows
+        if (tan)
+            for (int n = 0; n <= N; ++n) {
+                const TanEntry<R> e = tan_entry<R>(n < N ? cs[n].c : R(0), D);
+                csw[n] = e.t; csw[NP + n] = e.al; csw[2 * NP + n] = e.be;
+            }
         for (int bi = 0; bi < lay.brows; ++bi)
             for (int k = 0; k < G_k; ++k) {
                 const int b = bi * G_k + k;
@@ -132,7 +153,7 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                 for (int r = 0; r < G_r; ++r) {
                     set_amp(acc[r], 0.0);
                     for (int pi = 0; pi < lay.passes; ++pi) {
-                        R cx[U], sx[U], cw[U], sw[U];
+                        R cx[U], sx[U], cw[U], sw[U], tx[U], ax[U], bx[U];
                         int deg[U];
                         const int g = k * G_r + r;
                         for (int u = 0; u < U; ++u) {
@@ -141,13 +162,24 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                             int xo = xotab[sl];
                             deg[u] = MODE == 1 ? (xo >> 24) : 0;
                             if (MODE == 1) xo &= 0xFFFFFF;
-                            const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + xo);
-                            cx[u] = e.c; sx[u] = e.s;
+                            if (tan) {
+                                const R* e = reinterpret_cast<const R*>(reinterpret_cast<const char*>(csw.data()) + xo);
+                                tx[u] = e[0]; ax[u] = e[NP]; bx[u] = e[2 * NP];
+                                cx[u] = sx[u] = 0;
+                            } else {
+                                const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + xo);
+                                cx[u] = e.c; sx[u] = e.s;
+                                tx[u] = ax[u] = bx[u] = 0;
+                            }
                         }
                         A init[4];
                         for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
-                        A part = evolve_blocks<A, R, U, MODE>(init, cx, sx, cw, sw, deg, D);
-                        if (lay.passes == 1) acc[r] = part; else add_amp(acc[r], part);
+                        if (tan) {
+                            TanRun<A, R, U, 16>::go(D, init, tx, ax, bx, cw, sw, acc[r]);
+                        } else {
+                            A part = evolve_blocks<A, R, U, MODE>(init, cx, sx, cw, sw, deg, D);
+                            if (lay.passes == 1) acc[r] = part; else add_amp(acc[r], part);
+                        }
                     }
                 }
                 for (int m = G_r >> 1; m >= 1; m >>= 1) {
@@ -169,11 +201,11 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
 }
 
 // amp: 0 c128, 1 c64, 2 r64
-extern "C" int qkan_emu_block_forward(int amp, int mode, int min_g, const double* x, const double* W, long long B, int N, int K,
-                                      int D, double* out, double* amps) {
+extern "C" int qkan_emu_block_forward(int amp, int mode, int min_g, int tan, const double* x, const double* W, long long B, int N,
+                                      int K, int D, double* out, double* amps) {
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
 #define BCASE(AMP, A, R, MODE, UU) \
-    if (amp == AMP && mode == MODE && lay.U == UU) return emu_block<A<R>, R, UU, MODE>(x, W, B, N, K, D, min_g, out, amps);
+    if (amp == AMP && mode == MODE && lay.U == UU) return emu_block<A<R>, R, UU, MODE>(x, W, B, N, K, D, min_g, tan, out, amps);
     BCASE(0, Cplx, double, 0, 4) BCASE(0, Cplx, double, 0, 2) BCASE(0, Cplx, double, 0, 1)
     BCASE(0, Cplx, double, 1, 4) BCASE(0, Cplx, double, 1, 2) BCASE(0, Cplx, double, 1, 1)
     BCASE(1, Cplx, float, 0, 4) BCASE(1, Cplx, float, 0, 2) BCASE(1, Cplx, float, 0, 1)

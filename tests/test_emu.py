@@ -49,17 +49,23 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
     """qkan_block.cuh (layout planner, table entries, block evolution, xor-butterfly read-out) run lane by lane."""
     import ctypes
     f = emu.qkan_emu_block_forward
-    f.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
     rng = np.random.default_rng(N * 31 + K * 7 + D + min_g)
     B = 3
     x = rng.uniform(-1.2, 1.2, (B, N))
     x[1] = 0.0
+    if N >= 4:
+        x[2, :4] = [np.sqrt(0.5), -np.sqrt(0.5), 1e-300, -1.0]      # the quarter-turn boundary, a tiny and a unit input
     W = rng.uniform(-1, 1, (D + 1, N * K))
     spec = o.circuit_spec(N, K, D)
-    for amp, mode, tol in ((0, 0, 1e-14), (0, 1, 1e-14), (1, 0, 1e-5), (2, 0, 1e-14)):
+    tan_ok = 2 <= D <= 16            # scaled-rotation form of the degree-specialised kernels (use_tan_form)
+    cases = [(0, 0, 0, 1e-14), (0, 1, 0, 1e-14), (1, 0, 0, 1e-5), (2, 0, 0, 1e-14)]
+    if tan_ok:
+        cases += [(0, 0, 1, 1e-14), (1, 0, 1, 1e-5), (2, 0, 1, 1e-14)]
+    for amp, mode, tan, tol in cases:
         out = np.zeros((B, K))
         amps = np.zeros((B, K, 2))
-        rc = f(amp, mode, min_g, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data)
+        rc = f(amp, mode, min_g, tan, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data)
         assert rc == 0
         ref = o.forward_closed_form(x, W, N, K, D, "paper" if mode else "compat")
         assert np.abs(out - ref).max() <= tol

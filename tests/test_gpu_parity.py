@@ -247,7 +247,8 @@ def test_c_abi_direct(Q):
     info = b.KernelInfo()
     assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
     assert info.qubits == 8 and info.flops_survey == 21504 and info.grid > 0
-    assert info.engine == 0 and info.blocks == 64 and info.flops_exec == 64 * (24 * 3 - 4)
+    assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 1 and info.flops_exec == 64 * (16 * 3 + 4)
+    assert info.fp_inst_exec == 64 * (8 * 3 + 4)
     lib.qkan_layer_destroy(h)
     assert b.measure_fma_peak(0, True) > 5.0
 

@@ -357,13 +357,13 @@ def run_ours(a):
         pipe_util = info["fp_inst_exec"] * B / (k_ms * 1e-3) / (peak * 1e12 / 2.0)
         io = (8 * a.N + 8 * a.K) * B
         # DRAM bytes per launch of the dominant kernel from the ncu --set full capture of this workload
-        # (profiles/r01_ncu_c2.txt: dram__bytes_read 32.03 MB + dram__bytes_write 0.28 MB; the 32 MB of outputs
+        # (profiles/r01c_ncu_c2.txt: dram__bytes_read 32.03 MB + dram__bytes_write 0.28 MB; the 32 MB of outputs
         # stay in the 126 MB L2).  Only known for the default workload.
         traffic = None
         if (a.N, a.K, a.D, a.batch, a.dtype, a.prep, a.mode) == (4, 4, 3, 1_000_000, "complex128", "analytic", "compat"):
             traffic = 32.03e6 + 0.28e6
         roofline = {"bound": "fp64" if fp64 else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r01_ncu_c2.txt (ncu --set full, per launch)" if traffic else None,
+                    "traffic": traffic, "traffic_source": "profiles/r01c_ncu_c2.txt (ncu --set full, per launch)" if traffic else None,
                     "kernel_ms": k_ms,
                     "fp_pipe_utilisation": pipe_util,
                     "flops_per_sample_executed": info["flops_exec"], "fp_instructions_per_sample": info["fp_inst_exec"],
@@ -373,8 +373,12 @@ def run_ours(a):
                     "peak_source": "qkan_measure_fma_peak: independent %s chains on all SMs, measured in this run" % ("DFMA" if fp64 else "FFMA"),
                     "hbm": {"algorithmic_bytes_per_sample": 8 * a.N + 8 * a.K, "achieved_gbs": io / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm,
                             "frac": io / (k_ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                    "note": "achieved = arithmetic the kernel really executes (DFMA=2, DMUL=DADD=1 flop; rotations are 6 flops in 4 "
-                            "instructions so 0.75 is the ceiling of frac at 100% pipe utilisation); *_survey_flops credits SURVEY 8(d) "
+                    "note": "achieved = arithmetic the kernel really executes (DFMA=2, DMUL=DADD=1 flop; "
+                            + ("scaled-rotation kernel: a CHEB pass is one FMA per real output - Ry = gamma*M(t), gamma^D and the quarter "
+                               "turns deferred to the last pass - so nearly every issue slot is an FMA"
+                               if info.get("scaled_rotations") else
+                               "rotations are 6 flops in 4 instructions so 0.75 is the ceiling of frac at 100% pipe utilisation")
+                            + "); *_survey_flops credits SURVEY 8(d) "
                             "F_alg = 6*S*P for the same time (the kernel prepares |+> in closed form, skips padded blocks and prunes the "
                             "last layer to the post-selected outputs, so it executes fewer flops than F_alg)"}
         # the literal Appendix-C simulation (prep="gates": every gate incl. the initial Hadamards is a pass over the

@@ -81,10 +81,10 @@ BLOCK_MINB = {
     (4, 1, 256): 2, (4, 1, 128): 4, (4, 1, 64): 8, (4, 1, 32): 16,
     (2, 1, 256): 3, (2, 1, 128): 6,
     (1, 1, 256): 4, (1, 1, 128): 8, (1, 1, 64): 16, (1, 1, 32): 32,
-    (1, 2, 256): 3, (1, 2, 128): 6,
+    (1, 2, 256): 3, (1, 2, 128): 5,
 }
 DT_MAX = 16     # compile-time degree specialisations (compat mode): D = 1 .. DT_MAX
-SU2_DT_MAX = 4  # two samples per lane only pay off for shallow sequences
+SU2_DT_MAX = 8  # two samples per lane only pay off for shallow sequences
 
 
 def block_instances():

@@ -103,8 +103,9 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const int want_SU = fSU ? fSU : (max_degree <= 4 ? 2 : 1);
         // the (cos, sin) pair, or the (t, alpha, beta) triple of the scaled-rotation kernels (wide rows skip the raw-x staging)
         const bool tan_dt = max_degree <= 16 && !getenv("QKAN_BLOCK_NO_DT");
-        const int NTs_a[4] = {256, 128, 64, 32}, NTs_b[4] = {128, 256, 64, 32};
-        const int* NTs = (want_SU == 2) ? NTs_b : NTs_a;
+        // 256-thread CTAs first (measured best or equal for SU = 1 and, with the scaled-rotation kernels, SU = 2:
+        // N4 K4 D3 0.174 -> 0.164 ms, gpurun_out/ab_c2.log)
+        const int NTs[4] = {256, 128, 64, 32};
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
             const int NT = NTs[ni];
             if (fNT && NT != fNT) continue;
@@ -228,12 +229,12 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                           l->bkern->tan ? 4 : 8, slots,
+                                                                           l->bkern->tan ? 12 : 8, slots,
                                                                            (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                            l->bkern->tan ? 8 : 16, slots,
+                                                                            l->bkern->tan ? 24 : 16, slots,
                                                                             (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);

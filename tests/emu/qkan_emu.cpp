@@ -129,8 +129,8 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
     std::vector<int> xotab(slots);
     for (long long e = 0; e < slots; ++e)
         fill_block_slot<R>(e, W, N, K, D, U, lay.passes, lay.g_r_log2, lay.g_k_log2, MODE, cstab.data(), xotab.data(),
-                           tan ? (int)sizeof(R) : (int)sizeof(CS<R>));
-    const int NP = tan ? cs_row_stride(N, G, (int)sizeof(R), 3) : N + 1;
+                           tan ? (int)sizeof(TanEntry<R>) : (int)sizeof(CS<R>));
+    const int NP = tan ? (tan_row_words(N, G, (int)sizeof(R)) + 2) / 3 : N + 1;   // emulation rows: whole triples
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
     while ((1 << NB) < K) ++NB;
@@ -140,12 +140,9 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
         std::vector<CS<R>> cs(N + 1);
         for (int n = 0; n < N; ++n) { R c = clip_unit<R>(x[s * N + n]); cs[n].c = c; cs[n].s = qk_sqrt((R(1) - c) * (R(1) + c)); }
         cs[N].c = 0; cs[N].s = 1;
-        std::vector<R> csw(3 * (size_t)NP, R(0));            // t | alpha | beta word rows
+        std::vector<TanEntry<R>> cst((size_t)NP);            // (t, alpha, beta) triples
         if (tan)
-            for (int n = 0; n <= N; ++n) {
-                const TanEntry<R> e = tan_entry<R>(n < N ? cs[n].c : R(0), D);
-                csw[n] = e.t; csw[NP + n] = e.al; csw[2 * NP + n] = e.be;
-            }
+            for (int n = 0; n <= N; ++n) cst[n] = tan_entry<R>(n < N ? cs[n].c : R(0), D);
         for (int bi = 0; bi < lay.brows; ++bi)
             for (int k = 0; k < G_k; ++k) {
                 const int b = bi * G_k + k;
@@ -163,8 +160,8 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                             deg[u] = MODE == 1 ? (xo >> 24) : 0;
                             if (MODE == 1) xo &= 0xFFFFFF;
                             if (tan) {
-                                const R* e = reinterpret_cast<const R*>(reinterpret_cast<const char*>(csw.data()) + xo);
-                                tx[u] = e[0]; ax[u] = e[NP]; bx[u] = e[2 * NP];
+                                const TanEntry<R>& e = *reinterpret_cast<const TanEntry<R>*>(reinterpret_cast<const char*>(cst.data()) + xo);
+                                tx[u] = e.t; ax[u] = e.al; bx[u] = e.be;
                                 cx[u] = sx[u] = 0;
                             } else {
                                 const CS<R>& e = *reinterpret_cast<const CS<R>*>(reinterpret_cast<const char*>(cs.data()) + xo);

@@ -104,6 +104,18 @@ def block_instances():
     return out
 
 
+WINDOW_CTAS = ((256, 4), (256, 3))   # (NT, MINB) of the window kernels (wide input rows, scaled-rotation form, D = 2 .. DT_MAX)
+
+
+def window_instances():
+    out = []   # (group, amp, NT, MINB, DT)
+    for amp in ("c128", "c64", "r64"):
+        for dt in range(2, DT_MAX + 1):
+            for (nt, minb) in WINDOW_CTAS:
+                out.append((f"block_{amp}_d{dt}", amp, nt, minb, dt))
+    return out
+
+
 def write_if_changed(path, text):
     """keep timestamps stable so that `make` only rebuilds what really changed"""
     if os.path.exists(path) and open(path).read() == text:
@@ -121,6 +133,9 @@ def main():
     bgroups = {}
     for it in binst:
         bgroups.setdefault(it[0], []).append(it)
+    wgroups = {}
+    for it in window_instances():
+        wgroups.setdefault(it[0], []).append(it)
     d = os.path.join(HERE, "instances")
     os.makedirs(d, exist_ok=True)
     import io
@@ -149,6 +164,9 @@ def main():
         for (_, amp, U, SU, MODE, NT, MINB, DT, dflt) in items:
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_block_info<{A}, {R}, {U}, {SU}, {MODE}, {NT}, {MINB}, {DT}>({dflt}));\n")
+        for (_, amp, NT, MINB, DT) in wgroups.get(g, []):
+            A, R, _sz = AMPS[amp]
+            fh.write(f"    reg.push_back(make_block_window_info<{A}, {R}, {NT}, {MINB}, {DT}>());\n")
         fh.write("}\n")
         wanted.add(f"inst_{g}.cu")
         write_if_changed(os.path.join(d, f"inst_{g}.cu"), fh.getvalue())

@@ -76,7 +76,8 @@ inline int tan_row_words(int N, int G, int word_bytes) {
 // registers -> most warps; measured best or equal on every BASELINE config, profiles/r01_tune_*),
 // fewer shuffle steps, more rows in parallel.
 // min_g_log2 lets the caller force wide groups (few samples per CTA) for very wide inputs.
-inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, int force_U = 0) {
+// max_gk_log2 caps the rows evolved in parallel (the window kernel wants few: its input window grows with them).
+inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, int force_U = 0, int max_gk_log2 = 5) {
     const long long rowlen = (long long)N * (D + 1);
     BlockLayout best{};
     double best_score = -1.0;
@@ -85,7 +86,7 @@ inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, in
         const int U = Us[ui];
         if (force_U && U != force_U) continue;
         for (int gr = 0; gr <= 5; ++gr) {
-            for (int gk = 0; gr + gk <= 5; ++gk) {
+            for (int gk = 0; gr + gk <= 5 && gk <= max_gk_log2; ++gk) {
                 if (gr + gk < min_g_log2) continue;
                 const long long G_r = 1ll << gr, G_k = 1ll << gk;
                 const long long passes = (rowlen + G_r * U - 1) / (G_r * U);
@@ -102,6 +103,28 @@ inline BlockLayout plan_block_layout(int N, int K, int D, int min_g_log2 = 0, in
         }
     }
     return best;
+}
+
+// Input window of a row step.  Output row b reads the inputs x[(a + N b) / K], a < N: a run of about N / K
+// consecutive entries, so row step bi (rows bi G_k .. bi G_k + G_k - 1) needs only the window
+// [lo, lo + len) of the sample's input row.  The window kernel builds its rotation entries per row step
+// instead of per sample, which divides the shared memory per sample by about K / G_k (N784 K10: 19 KB -> 3.8 KB).
+QK_HD void block_window(int N, int K, int g_k_log2, int bi, int* lo, int* len) {
+    const long long b0 = (long long)bi << g_k_log2;
+    long long b1 = b0 + (1ll << g_k_log2);
+    if (b1 > K) b1 = K;
+    const long long first = (b0 * N) / K, last = (b1 * N - 1) / K;
+    *lo = (int)first;
+    *len = (int)(last - first + 1);
+}
+inline int block_window_max(int N, int K, int g_k_log2, int brows) {
+    int w = 1;
+    for (int bi = 0; bi < brows; ++bi) {
+        int lo, len;
+        block_window(N, K, g_k_log2, bi, &lo, &len);
+        if (len > w) w = len;
+    }
+    return w;
 }
 
 struct BlockParams {
@@ -125,6 +148,7 @@ struct BlockParams {
     int sub;                    // sub-iterations per x tile
     int tma_ok;
     int direct_x;               // wide input rows: no raw-x staging buffers, the pre-pass reads x from global memory
+    int window;                 // window kernel: entries per cs row (the widest row-step window, block_window_max); 0 = off
     // derived launch constants (filled by launch_block; kept in the constant bank so that the kernel does
     // not spend registers or instructions on them)
     int G, G_r, G_k;            // lanes per sample / per row / rows in parallel
@@ -148,7 +172,8 @@ struct BlockParams {
 // rotate by theta = pi (c = 0) and read the row's dummy (0, 1) entry: they add exactly 0.
 template <typename R>
 QK_HD void fill_block_slot(long long slot, const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
-                           int g_k_log2, int paper, CS<R>* cstab, int* xotab, int x_entry_bytes = (int)sizeof(CS<R>)) {
+                           int g_k_log2, int paper, CS<R>* cstab, int* xotab, int x_entry_bytes = (int)sizeof(CS<R>),
+                           int window = 0) {
     const int g_log2 = g_r_log2 + g_k_log2;
     const int g = (int)(slot & ((1ll << g_log2) - 1));
     long long t = slot >> g_log2;
@@ -160,14 +185,17 @@ QK_HD void fill_block_slot(long long slot, const double* W, int N, int K, int D,
     const long long i = ((long long)(pi << g_r_log2) + r) * U + u;
     CS<R> q;
     q.c = R(0); q.s = R(1);
-    int xo = N * x_entry_bytes;                         // dummy entry (x = 0) at the end of every cs row
+    // dummy entry (x = 0) at the end of every cs row; window mode: rows hold the row step's input window only
+    int wlo = 0, wlen = 0;
+    if (window) block_window(N, K, g_k_log2, bi, &wlo, &wlen);
+    int xo = (window ? window : N) * x_entry_bytes;
     if (b < K && i < (long long)N * (D + 1)) {
         const int a = (int)(i / (D + 1)), d = (int)(i - (long long)a * (D + 1));
         const int flat = a + N * b;
         const R w = (R)W[(long long)d * N * K + flat];
         q.c = w;
         q.s = qk_sqrt((R(1) - w) * (R(1) + w));
-        xo = (flat / K) * x_entry_bytes;
+        xo = (flat / K - wlo) * x_entry_bytes;
         if (paper) xo |= d << 24;
     }
     cstab[slot] = q;
@@ -638,13 +666,126 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     }
 }
 
+// keep a kernel parameter in a register: without this the compiler re-reads the prepared block state from the
+// constant bank inside the pass loop (LDC, a long-scoreboard load: it was the top stall of the window kernel)
+__device__ __forceinline__ void keep_in_register(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void keep_in_register(float& v) { asm volatile("" : "+f"(v)); }
+
+// Window kernel: wide input rows (N784 K10: 6.3 KB of x, 19 KB of rotation triples per sample).  The entries of
+// a sample are built per ROW STEP from the step's input window (block_window) instead of once per sample, so a
+// CTA keeps tile * (W + 1) triples instead of tile * (N + 1) and shared memory no longer limits the resident
+// warps.  Scaled-rotation form, one block per lane at a time (U = 1, SU = 1); x is read straight from global
+// memory (each input is read once per row step that uses it: twice at most, at window boundaries).
+template <class A, typename R, int NT, int MINB, int DT>
+__global__ void __launch_bounds__(NT, MINB) qkan_block_window_kernel(const BlockParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int G = p.G, G_r = p.G_r;
+    const int SPC = p.SPC, tile = p.tile, RB = p.row_bytes, W = p.window;
+    constexpr size_t ENTB = sizeof(TanEntry<R>);
+    char* cs = reinterpret_cast<char*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int g = tid & (G - 1);
+    const int r = g & (G_r - 1);
+    const int k = g >> p.g_r_log2;
+    const int slot = tid >> (p.g_r_log2 + p.g_k_log2);
+    const CS<R>* __restrict__ cstab = reinterpret_cast<const CS<R>*>(p.cstab);
+    const int* __restrict__ xotab = p.xotab;
+
+    for (int i = tid; i < tile; i += NT)                      // the dummy entries never change
+        *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + W * ENTB) = tan_entry<R>(R(0), DT);
+    A init[4];
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        init[q].re = (R)p.init[2 * q];
+        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
+    }
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        keep_in_register(init[q].re);
+        if constexpr (A::is_complex) keep_in_register(init[q].im);
+    }
+    const long long n_it = (p.B + tile - 1) / tile;
+    const size_t step_slots = (size_t)p.passes * G;           // table entries of one row step
+
+    for (long long it = blockIdx.x; it < n_it; it += gridDim.x) {
+        const long long s0 = it * tile;
+        const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
+        const int nsub = (nsamp + SPC - 1) / SPC;
+        int prev_hi = -1;
+        for (int bi = 0; bi < p.brows; ++bi) {
+            int lo, len;
+            block_window(p.N, p.K, p.g_k_log2, bi, &lo, &len);
+            __syncthreads();                                  // the previous row step's entries are consumed
+            // pre-pass over the window of every sample of the tile (flat walk, no division in the loop): range count
+            // (ChebyshevStep.py:46-49; an input shared by two windows is counted once), clip (:52), entry
+            unsigned bad = 0;
+            {
+                const int n_in = nsamp * len;
+                int row = tid / len, j = tid - row * len;
+                const int dr = NT / len, dj = NT - dr * len;
+                const double* xw = p.x + s0 * p.N + lo;
+                for (int e = tid; e < n_in; e += NT) {
+                    const double v = xw[(size_t)row * p.N + j];
+                    if (lo + j > prev_hi && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
+                    *reinterpret_cast<TanEntry<R>*>(cs + (size_t)row * RB + j * ENTB) = tan_entry<R>(clip_unit<R>(v), DT);
+                    j += dj;
+                    row += dr;
+                    if (j >= len) { j -= len; ++row; }
+                }
+            }
+            prev_hi = lo + len - 1;
+            if (bad) atomicAdd(p.oor, (unsigned long long)bad);
+            __syncthreads();
+
+            const int b = (bi << p.g_k_log2) + k;
+            const CS<R>* cp0 = cstab + (size_t)bi * step_slots + g;
+            const int* xp0 = xotab + (size_t)bi * step_slots + g;
+            const CS<R> q0 = cp0[0];
+            const int x0 = xp0[0];
+            int ls = slot;
+            for (int si = 0; si < nsub; ++si, ls += SPC) {
+                const char* row = cs + (size_t)ls * RB;       // idle slots of a ragged tile evolve a stale row; nothing is stored
+                const CS<R>* cp = cp0;
+                const int* xp = xp0;
+                CS<R> qn = q0;
+                int xn = x0;
+                A acc;
+                set_amp(acc, 0.0);
+                for (int pi = 0; pi < p.passes; ++pi) {
+                    const R cw[1] = {qn.c}, sw[1] = {qn.s};
+                    const TanEntry<R>* e = reinterpret_cast<const TanEntry<R>*>(row + xn);
+                    cp += G;
+                    xp += G;
+                    qn = cp[0];                               // next pass (the tables end with one pass of padding slots)
+                    xn = xp[0];
+                    const R t[1] = {e->t}, al[1] = {e->al}, be[1] = {e->be};
+                    evolve_blocks_tan<A, R, 1, DT>(init, t, al, be, cw, sw, acc);
+                }
+                // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
+                for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
+                if (ls < nsamp && r == 0 && b < p.K) {
+                    const long long o = (p.row0 + s0 + ls) * p.K + b;
+                    store_result(p, o, (double)acc.re * p.out_scale);
+                    if (p.amps) {
+                        Cplx<R> z;
+                        z.re = (R)((double)acc.re * p.amp_scale);
+                        if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
+                        else z.im = R(0);
+                        reinterpret_cast<Cplx<R>*>(p.amps)[(s0 + ls) * p.K + b] = z;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <typename R>
 __global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
-                                                 int g_k_log2, int paper, int x_entry_bytes, long long slots_total,
+                                                 int g_k_log2, int paper, int x_entry_bytes, int window, long long slots_total,
                                                  CS<R>* cstab, int* xotab, unsigned long long* bad_weights) {
     const long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= slots_total) return;
-    fill_block_slot<R>(slot, W, N, K, D, U, passes, g_r_log2, g_k_log2, paper, cstab, xotab, x_entry_bytes);
+    fill_block_slot<R>(slot, W, N, K, D, U, passes, g_r_log2, g_k_log2, paper, cstab, xotab, x_entry_bytes, window);
     // |w| <= 1 is required for the rotation to exist (MulStep.py:36-37): check each weight once
     if (slot < (long long)N * K * (D + 1)) {
         const double w = W[slot];
@@ -656,7 +797,8 @@ struct BlockKernelInfo {
     int amp, mode, U, NT, MINB;
     int SU;                     // samples per lane at a time
     int DT;                     // 0 = any D (run-time loop), else only for D == DT
-    int tan;                    // scaled-rotation form (use_tan_form): cs rows are t | alpha | beta word rows
+    int tan;                    // scaled-rotation form (use_tan_form): cs rows hold (t, alpha, beta) triples
+    int window;                 // window kernel (wide input rows): entries are built per row step
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
@@ -739,7 +881,51 @@ BlockKernelInfo make_block_info(int is_default) {
     k.amp = AmpId<A>::v;
     k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
     k.tan = use_tan_form(MODE, DT, U) ? 1 : 0;
+    k.window = 0;
     k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
+    return k;
+}
+template <class A, typename R, int NT, int MINB, int DT>
+cudaError_t launch_block_window(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p0.D != DT || p0.window < 1) return cudaErrorInvalidValue;
+    auto kern = qkan_block_window_kernel<A, R, NT, MINB, DT>;
+    BlockParams p = p0;
+    const int SPC = NT / G;
+    p.row_bytes = tan_row_words(p.window, G, (int)sizeof(R)) * (int)sizeof(R);
+    int sub = (int)(32768 / ((size_t)SPC * p.row_bytes));      // about 32 KiB of rotation triples per CTA
+    if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
+    if (sub > 32) sub = 32;
+    if (sub < 1) sub = 1;
+    auto smem_for = [&](int sb) { return (size_t)SPC * sb * p.row_bytes; };
+    if (smem_for(sub) > 200 * 1024) return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(sub));
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_for(sub));
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const long long resident = (long long)sm_count * per_sm;
+    while (sub > 1 && (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub) < 4 * resident) sub >>= 1;
+    const long long n_it = (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub);
+    long long grid = resident < n_it ? resident : n_it;
+    if (grid < 1) grid = 1;
+    p.sub = sub;
+    p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
+    p.SPC = SPC; p.tile = SPC * sub;
+    p.tma_ok = 0; p.direct_x = 1; p.s_tot = -1;
+    if (grid_out) *grid_out = (int)grid;
+    if (smem_out) *smem_out = (int)smem_for(sub);
+    kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
+    return cudaGetLastError();
+}
+template <class A, typename R, int NT, int MINB, int DT>
+BlockKernelInfo make_block_window_info() {
+    BlockKernelInfo k;
+    k.amp = AmpId<A>::v;
+    k.mode = 0; k.U = 1; k.SU = 1; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = 1;
+    k.tan = 1;
+    k.window = 1;
+    k.launch = &launch_block_window<A, R, NT, MINB, DT>;
     return k;
 }
 #endif  // __CUDACC__

@@ -62,6 +62,7 @@ struct qkan_layer {
     const KernelInfo* kern = nullptr;         // staged
     const BlockKernelInfo* bkern = nullptr;   // block
     BlockLayout lay{};
+    int window = 0;                           // window kernel: widest row-step input window (entries per cs row)
     void* wtab = nullptr;
     int* xidx = nullptr;
     unsigned long long* counters = nullptr;   // [0] out-of-range x, [1] |w| > 1
@@ -91,6 +92,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     const KernelInfo* best = nullptr;
     const BlockKernelInfo* bbest = nullptr;
     BlockLayout lay{};
+    int window = 0;
     if (prep == QKAN_PREP_ANALYTIC) {
         // block engine: any N, K, D.  Pick the lane layout and the CTA size whose x tile fits.
         if ((long long)N * K >= (1 << 20) || max_degree >= 2048 || (mode == QKAN_MODE_PAPER && max_degree >= 128))
@@ -127,7 +129,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 if (cs_bytes_for(cand.U) > 72 * 1024) continue;
                 const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
-                    if (k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
+                    if (k.window || k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
                     if (k.SU != ((cand.U == 1 && (NT == 256 || NT == 128)) ? want_SU : 1)) continue;
                     if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
                     if (k.DT == max_degree && !getenv("QKAN_BLOCK_NO_DT")) { bbest = &k; break; }   // degree-specialised
@@ -137,6 +139,36 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 if (bbest) lay = cand;
             }
         }
+        // wide input rows (the main path found nothing, or had to fall back to the U = 4 (cos, sin) kernels because
+        // the rotation entries of whole input rows left room for < 24 warps per SM): the window kernel builds the
+        // entries per row step from the step's input window (N784 K10 D5: 4.0 -> 6.3 M samples/s).  Scaled-rotation
+        // form only (compat mode, 2 <= D <= 16).
+        if (use_tan_form(mode, tan_dt ? max_degree : 0, 1) && fU <= 1 && !getenv("QKAN_BLOCK_NO_WINDOW")) {
+            const bool bound = !bbest || bbest->U == 4;
+            // narrowest lane group whose window tile leaves room for four (else three) 256-thread CTAs per SM
+            // (rows in parallel capped first at 1, then 2, ...: the window grows with them)
+            for (int want = 32; want >= 24 && bound && !window; want -= 8)
+            for (int gkm = 0; gkm <= 5 && !window; ++gkm)
+            for (int mg = 0; mg <= 5 && !window; ++mg) {
+                const BlockLayout c = plan_block_layout(N, K, max_degree, mg, 1, gkm);
+                const int G = 1 << (c.g_r_log2 + c.g_k_log2);
+                if (G < (1 << mg) || c.efficiency < 0.9) continue;
+                const int W = block_window_max(N, K, c.g_k_log2, c.brows);
+                const size_t win_cs = (size_t)(256 / G) * (W + 1) * 3 * amp_real_size(dtype);
+                if ((220 * 1024 / (win_cs + 1024)) * 8 < (size_t)want) continue;
+                for (const BlockKernelInfo& k : block_registry()) {
+                    if (!k.window || k.amp != dtype || k.DT != max_degree) continue;
+                    if (fNT && k.NT != fNT) continue;
+                    if (fMINB && k.MINB != fMINB) continue;
+                    bbest = &k; lay = c; window = W;
+                    break;
+                }
+            }
+        }
+        if (getenv("QKAN_DEBUG_SELECT") && bbest)
+            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
+                    N, K, max_degree, dtype, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
+                    lay.g_r_log2, lay.g_k_log2, lay.passes, lay.brows);
         if (!bbest) {
             char buf[160];
             snprintf(buf, sizeof buf, "no block kernel for N=%d K=%d D=%d dtype=%d mode=%d (input row too wide for shared memory?)",
@@ -169,6 +201,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     l->kern = best;
     l->bkern = bbest;
     l->lay = lay;
+    l->window = window;
     l->engine = (prep == QKAN_PREP_ANALYTIC) ? 0 : 1;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
@@ -180,7 +213,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
     if (l->engine == 0) {
         // + one pass of padding slots: the streaming kernel prefetches one pass ahead
         const size_t G = (size_t)1 << (l->lay.g_r_log2 + l->lay.g_k_log2);
-        const size_t slots = ((size_t)l->lay.brows * l->lay.passes + 1) * l->lay.U * G;
+        // (+ 8 more, never read: the window kernel's L1 prefetches run WINDOW_PREFETCH passes ahead)
+        const size_t slots = ((size_t)l->lay.brows * l->lay.passes + 1 + 8) * l->lay.U * G;
         e = cudaMalloc(&l->wtab, slots * 2 * amp_real_size(dtype));
         if (e == cudaSuccess) e = cudaMalloc(&l->xidx, slots * sizeof(int));
     } else {
@@ -229,12 +263,12 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                           l->bkern->tan ? 12 : 8, slots,
+                                                                           l->bkern->tan ? 12 : 8, l->window, slots,
                                                                            (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                            l->bkern->tan ? 24 : 16, slots,
+                                                                            l->bkern->tan ? 24 : 16, l->window, slots,
                                                                             (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);
@@ -274,7 +308,7 @@ static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, voi
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
-        p.sub = 1; p.tma_ok = 0; p.direct_x = 0;
+        p.sub = 1; p.tma_ok = 0; p.direct_x = 0; p.window = l->window;
         for (int q = 0; q < 8; ++q) p.init[q] = 0.0;
         p.init[0] = 1.0;                                   // PREPARE'd block state (1, 0, 0, 0), un-normalised
         p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
@@ -446,6 +480,7 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         info->flops_exec = cf * (double)info->blocks * (l->D > 0 ? 24.0 * Dd - 4.0 : 8.0);
         info->fp_inst_exec = cf * (double)info->blocks * (l->D > 0 ? 16.0 * Dd - 2.0 : 6.0);
         info->scaled_rotations = k.tan;
+        info->input_window = l->window;
         if (k.tan) {
             // scaled-rotation form (evolve_blocks_tan): D-1 full passes of 8 FMA, the pruned last pass
             // alpha u + beta v (4 MUL + 4 FMA), SELECT fused with the read-out sum (4 FMA)

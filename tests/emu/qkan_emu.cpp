@@ -117,19 +117,22 @@ template <class A, typename R, int U> struct TanRun<A, R, U, 1> {
     static void go(int, const A (&)[4], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], A&) {}
 };
 
-// tan != 0: the scaled-rotation form of the degree-specialised kernels (compat mode, 2 <= D <= 16)
+// tan != 0: the scaled-rotation form of the degree-specialised kernels (compat mode, 2 <= D <= 16);
+// tan == 2: the window kernel's tables and per-row-step input windows (U = 1 layouts only)
 template <class A, typename R, int U, int MODE>
 int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, int tan, double* out, double* amps) {
     if (tan && (MODE != 0 || D < TAN_MIN_DT || D > 16)) return -4;
+    if (tan == 2 && U != 1) return -5;
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
     if (lay.U != U) return -3;
     const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
     const long long slots = ((long long)lay.brows * lay.passes + 1) * U * G;
+    const int window = tan == 2 ? block_window_max(N, K, lay.g_k_log2, lay.brows) : 0;
     std::vector<CS<R>> cstab(slots);
     std::vector<int> xotab(slots);
     for (long long e = 0; e < slots; ++e)
         fill_block_slot<R>(e, W, N, K, D, U, lay.passes, lay.g_r_log2, lay.g_k_log2, MODE, cstab.data(), xotab.data(),
-                           tan ? (int)sizeof(TanEntry<R>) : (int)sizeof(CS<R>));
+                           tan ? (int)sizeof(TanEntry<R>) : (int)sizeof(CS<R>), window);
     const int NP = tan ? (tan_row_words(N, G, (int)sizeof(R)) + 2) / 3 : N + 1;   // emulation rows: whole triples
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
@@ -143,7 +146,15 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
         std::vector<TanEntry<R>> cst((size_t)NP);            // (t, alpha, beta) triples
         if (tan)
             for (int n = 0; n <= N; ++n) cst[n] = tan_entry<R>(n < N ? cs[n].c : R(0), D);
-        for (int bi = 0; bi < lay.brows; ++bi)
+        for (int bi = 0; bi < lay.brows; ++bi) {
+            if (window) {                                    // the row step's window of the input row, dummy at index `window`
+                int lo, len;
+                block_window(N, K, lay.g_k_log2, bi, &lo, &len);
+                if (len > window) return -6;
+                cst.assign((size_t)window + 1, TanEntry<R>{R(7), R(7), R(7)});   // stale entries must never be read
+                for (int j = 0; j < len; ++j) cst[j] = tan_entry<R>(cs[lo + j].c, D);
+                cst[window] = tan_entry<R>(R(0), D);
+            }
             for (int k = 0; k < G_k; ++k) {
                 const int b = bi * G_k + k;
                 std::vector<A> acc(G_r);
@@ -193,6 +204,7 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
                     }
                 }
             }
+        }
     }
     return 0;
 }

@@ -62,6 +62,11 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
     cases = [(0, 0, 0, 1e-14), (0, 1, 0, 1e-14), (1, 0, 0, 1e-5), (2, 0, 0, 1e-14)]
     if tan_ok:
         cases += [(0, 0, 1, 1e-14), (1, 0, 1, 1e-5), (2, 0, 1, 1e-14)]
+        lay6 = (ctypes.c_int * 6)()
+        eff = ctypes.c_double()
+        emu.qkan_emu_block_layout(N, K, D, min_g, lay6, ctypes.byref(eff))
+        if lay6[0] == 1:             # U = 1 layouts: the window kernel's tables and per-row-step windows
+            cases += [(0, 0, 2, 1e-14), (1, 0, 2, 1e-5)]
     for amp, mode, tan, tol in cases:
         out = np.zeros((B, K))
         amps = np.zeros((B, K, 2))

@@ -152,6 +152,33 @@ def test_oracle_parity_seeded(Q, N, K, D):
         assert np.abs(a - amps).max() <= 1e-14                                 # post-selected amplitudes
 
 
+@pytest.mark.parametrize("N,K,D", [(784, 10, 5), (1000, 3, 2), (600, 16, 4), (2000, 1, 3), (513, 7, 16), (900, 33, 2), (100, 10, 5)])
+def test_window_kernel_wide_rows(Q, N, K, D):
+    """Wide input rows run the window kernel (rotation entries built per row step from the step's input window)."""
+    rng = np.random.default_rng(N + 3 * K + D)
+    B = 61                                    # ragged
+    x = rng.uniform(-1.1, 1.1, (B, N))
+    x[2] = 0.0
+    x[3, ::2] = 1.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    ref = o.forward_closed_form(x, W, N, K, D)
+    n_bad = int(((x < -1 - 1e-8) | (x > 1 + 1e-8)).sum())
+    for dtype in ("complex128", "complex64", "real64"):
+        layer = Q.QKANLayer(N, K, D, dtype=dtype)
+        y, a = layer.forward(x, W, return_amplitudes=True)
+        info = layer.kernel_info()
+        if K > 1:                                          # K = 1: the one output row reads every input, no window to cut
+            assert info["scaled_rotations"] == 1, info
+        assert_close(y, ref, dtype)
+        layer.forward(torch.from_numpy(x).cuda(), W)       # device input: the count stays for the caller
+        assert layer.out_of_range_count() == n_bad         # an input shared by two windows is counted once
+        spec = o.circuit_spec(N, K, D)
+        assert_close(np.real(a) * spec.out_scale, ref, dtype)
+    big = Q.QKANLayer(N, K, D)                              # several tiles per CTA, ragged tail
+    xb = rng.uniform(-1, 1, (3001, N))
+    assert_close(big.forward(xb, W), o.forward_closed_form(xb, W, N, K, D))
+
+
 @pytest.mark.parametrize("N,K,D", [(4, 4, 3), (8, 8, 5), (3, 2, 4), (5, 3, 1)])
 def test_paper_mode(Q, N, K, D):
     rng = np.random.default_rng(N + K + D)

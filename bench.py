@@ -324,8 +324,10 @@ def run_ours(a):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / float(te.item()), "unit": "samples/s", "h2d_bytes_per_step": B * a.N * 8,
                "d2h_bytes_per_step": B * a.K * 8, "steps": n_e2e,
-               "how": "QKANLayer.forward(numpy view of pinned host x, out=pinned host y): chunked H2D / kernel / D2H "
-                      "overlapped on 3 streams, wall clock over the call incl. final sync, per rank, max over ranks"}
+               "how": "QKANLayer.forward(numpy view of pinned host x, out=pinned host y), wall clock over the calls incl. the "
+                      "final sync, per rank, max over ranks.  Pinned buffers: the kernel itself streams x from host memory "
+                      "(TMA bulk loads over PCIe) and stores the results into the host buffer - no staging copies; pageable "
+                      "buffers: chunked H2D / kernel / D2H on 3 streams (QKAN_HOST_PATH=staged forces that path)"}
         assert np.array_equal(on, outs[0].cpu().numpy()), "host path and device path disagree"
 
     if rank == 0:

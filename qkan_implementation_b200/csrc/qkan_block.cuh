@@ -411,6 +411,11 @@ __device__ __forceinline__ void store_result(const BlockParams& p, long long idx
     }
 }
 
+// keep a kernel parameter in a register: without this the compiler re-reads the prepared block state from the
+// constant bank inside the pass loop (LDC, a long-scoreboard load: it was the top stall of the window kernel)
+__device__ __forceinline__ void keep_in_register(double& v) { asm volatile("" : "+d"(v)); }
+__device__ __forceinline__ void keep_in_register(float& v) { asm volatile("" : "+f"(v)); }
+
 template <class A> __device__ __forceinline__ A shfl_xor_amp(const A& a, int m) {
     A r;
     r.re = __shfl_xor_sync(0xffffffffu, a.re, m);
@@ -500,6 +505,13 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
         init[q].re = (R)p.init[2 * q];
         if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
     }
+#ifdef QKAN_PIN_INIT       // A/B-tested on this kernel (its tables are L1 resident): no measurable difference, left off
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        keep_in_register(init[q].re);
+        if constexpr (A::is_complex) keep_in_register(init[q].im);
+    }
+#endif
     // per-lane view of the slot tables: entry of (bi, pi, u) sits ((bi * passes + pi) * U + u) * G after `g`
     R cw[U], sw[U];
     int xoff[U], deg[U];
@@ -666,10 +678,6 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     }
 }
 
-// keep a kernel parameter in a register: without this the compiler re-reads the prepared block state from the
-// constant bank inside the pass loop (LDC, a long-scoreboard load: it was the top stall of the window kernel)
-__device__ __forceinline__ void keep_in_register(double& v) { asm volatile("" : "+d"(v)); }
-__device__ __forceinline__ void keep_in_register(float& v) { asm volatile("" : "+f"(v)); }
 
 // Window kernel: wide input rows (N784 K10: 6.3 KB of x, 19 KB of rotation triples per sample).  The entries of
 // a sample are built per ROW STEP from the step's input window (block_window) instead of once per sample, so a

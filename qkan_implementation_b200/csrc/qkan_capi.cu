@@ -401,6 +401,32 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     if (B == 0) return QKAN_OK;
     if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
     CU(cudaSetDevice(l->device));
+    // Pinned (page-locked, device-mapped) host buffers: no staging copies at all.  The kernel streams x from
+    // host memory itself (the same 1-D TMA bulk loads, two tiles in flight per CTA) and stores every result
+    // straight into the host buffer, so input and output cross PCIe concurrently with the arithmetic and there is
+    // no chunk pipeline to fill and drain.  Pageable buffers take the staged path below.
+    {
+        auto mapped = [](const void* ptr, void** dev) -> bool {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+            *dev = at.devicePointer;
+            return true;
+        };
+        void *dx = nullptr, *dout = nullptr, *damps = nullptr;
+        const char* mode_env = getenv("QKAN_HOST_PATH");          // "staged" forces the copy pipeline (A/B aid)
+        const bool want_zero_copy = !(mode_env && strcmp(mode_env, "staged") == 0);
+        if (want_zero_copy && mapped(x, &dx) && mapped(out, &dout) && (!amps || mapped(amps, &damps))) {
+            if (!l->s_k) {
+                int rc0 = ensure_host_path(l, 0, false);
+                if (rc0) return rc0;
+            }
+            int rc = launch_on(l, (const double*)dx, B, (double*)dout, damps, l->s_k);
+            if (rc) return rc;
+            CU(cudaStreamSynchronize(l->s_k));
+            return QKAN_OK;
+        }
+    }
     int rc = ensure_host_path(l, B, amps != nullptr);
     if (rc) return rc;
     // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile

@@ -135,6 +135,28 @@ int qkan_forward(const void* x, const void* w, void* out, int64_t B, int N, int 
 int qkan_simulate_circuit(const int* gates, const double* params, int n_gates, int n_qubits,
                           const long long* basis, int64_t n_states, void* state_out, void* cuda_stream);
 
+/* ---- DegreeOptimizer.evaluate_degree (original_degree_optimizer/DegreeOptimizer.py:122-158).
+ * Chebyshev features T_k(clip(x, -1, 1)), k = 0..D (ChebyshevStep.py:32-53) of x [n, F] (row-major, device),
+ * columns in the reference's np.hstack order: column k F + f; P = F (D+1).
+ *
+ * qkan_cheb_gram: G [(P+1), (P+1)] (device, row-major) = A^T A of the augmented matrix A = [X_D | y]: its
+ *   leading F (d+1) block is X_d^T X_d for every d <= D, column P holds X_D^T y, and G[P][P] = y^T y.  Fused
+ *   feature generation + FP64 tensor-core (DMMA) SYRK; partial tiles are summed in a fixed order, so the result is
+ *   deterministic.  `workspace` (device) must hold qkan_cheb_gram_workspace() bytes.  0 <= D <= 16.
+ * qkan_cheb_residuals: explicit residuals r_d = y - X_d c_d of all D+1 fits in one pass.  coef [D+1][P] (device;
+ *   zero where a column's degree exceeds d), w [n] sample weights or NULL, ybar = mean(y).  Per CTA c (count from
+ *   qkan_cheb_residuals_ctas) partial sums, to be added up by the caller in CTA order:
+ *     sums [ctas][D+1][2] = {sum r_d^2, sum w r_d^2};   tail [ctas][4] = {sum (y - ybar)^2, sum w y^2, sum w, sum y};
+ *     xtr  [ctas][D+1][P] = X_D^T r_d (NULL to skip; used for one step of iterative refinement).
+ * qkan_cheb_features: out [D+1][n][F] = the reference's transforms[d] (DegreeOptimizer.py:96-119). */
+int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes, int* slices);
+int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F, int D, double* G, void* workspace,
+                   int64_t workspace_bytes, void* cuda_stream);
+int qkan_cheb_residuals_ctas(int* ctas);
+int qkan_cheb_residuals(const double* x, const double* y, const double* w, int64_t n, int F, int D, const double* coef,
+                        double ybar, double* sums, double* tail, double* xtr, void* cuda_stream);
+int qkan_cheb_features(const double* x, int64_t n, int F, int D, double* out, void* cuda_stream);
+
 /* Measured peaks used as roofline denominators: dependent-free FMA chains on every SM.
  * fp64 != 0: DFMA, else FFMA.  Returns TFLOP/s (2 flops per FMA). */
 int qkan_measure_fma_peak(int device, int fp64, double* tflops);

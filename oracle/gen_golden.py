@@ -100,7 +100,80 @@ def main():
     ms2.set_weights(2, np.array([.5, .5, -.5, -.5]))
     m2 = ms2.get_weighted_polynomial_matrix(np.array([.5, -.5]), 2, 2)
     np.savez(os.path.join(GOLDEN, "kat_steps.npz"), t2=t2, dil=dil, mul_deg1=m1, mul_deg2=m2)
+    degree_goldens(QKANLayer)
     print("golden vectors written to", os.path.normpath(GOLDEN))
+
+
+class _Frame:
+    """What DegreeOptimizer needs of a polars DataFrame: to_numpy() and a schema whose str() is a cache key."""
+
+    def __init__(self, a):
+        self.a = np.asarray(a, dtype=np.float64)
+        self.schema = {f"feature_{i:02d}": "Float64" for i in range(self.a.shape[1])}
+
+    def to_numpy(self):
+        return self.a
+
+
+def import_reference_degree_optimizer():
+    """The unmodified original_degree_optimizer/DegreeOptimizer.py.  Its top-level imports of polars, pyqubo,
+    cpp_pyqubo and neal (DegreeOptimizer.py:3-6, BaseOptimizer.py:4) are not installed here and are only used by the
+    QUBO search (optimize_layer) and the cross-validation helpers, which the fixtures do not call: empty stubs."""
+    for name, attrs in {"polars": ["DataFrame", "col"], "cpp_pyqubo": ["Constraint"], "pyqubo": ["Array"],
+                        "neal": ["SimulatedAnnealingSampler"]}.items():
+        mod = types.ModuleType(name)
+        for a in attrs:
+            setattr(mod, a, None)
+        sys.modules.setdefault(name, mod)
+    sys.path.insert(0, os.path.join(REF, "original_degree_optimizer"))
+    from DegreeOptimizer import DegreeOptimizer  # noqa
+    return DegreeOptimizer
+
+
+def degree_goldens(QKANLayer):
+    """DegreeOptimizer.evaluate_degree / is_degree_definitive / fit's weight vectors / predict (row by row)."""
+    DegreeOptimizer = import_reference_degree_optimizer()
+    cases = [  # (name, n, F, D, weighted, noise)
+        ("a", 600, 5, 3, False, 0.05), ("b", 600, 5, 3, True, 0.05), ("c", 2500, 12, 4, True, 0.3),
+        ("d", 300, 79, 2, False, 0.1), ("e", 1000, 3, 8, True, 0.01)]
+    for name, n, F, D, weighted, noise in cases:
+        rng = np.random.default_rng(100 + len(name) + n + F + D)
+        x = rng.normal(0.0, 0.6, (n, F))                      # z-score like: a few percent beyond [-1, 1] get clipped
+        y = np.cos(2.0 * x[:, 0]) + 0.3 * x[:, 1 % F] ** 3 - 0.2 * x[:, 2 % F] + noise * rng.normal(size=n)
+        w = rng.uniform(0.5, 2.0, n) if weighted else None
+        opt = DegreeOptimizer([F, 2], D)
+        with contextlib.redirect_stdout(io.StringIO()):
+            scores, comp_r2 = opt.evaluate_degree(_Frame(x), y, w)
+            definitive, best = opt.is_degree_definitive(scores)
+        np.savez(os.path.join(GOLDEN, f"degree_eval_{name}.npz"), x=x, y=y, w=(w if weighted else np.zeros(0)),
+                 D=np.array(D), scores=scores, comp_r2=comp_r2, definitive=np.array(definitive), best=np.array(best),
+                 significance_threshold=np.array(opt.significance_threshold))
+        print(f"degree_eval_{name}: n={n} F={F} D={D} weighted={weighted} scores={scores}")
+    # fit's weight construction (DegreeOptimizer.py:63-76) and predict (:78-95), the latter row by row because the
+    # reference's own 2-D call raises (MulStep.py:62-66)
+    rng = np.random.default_rng(5)
+    N, K, D = 6, 3, 3
+    degrees = [[int(v) for v in rng.integers(0, D + 1, N)] for _ in range(K)]
+    xs = rng.normal(0.3, 1.5, (40, N))
+    opt = DegreeOptimizer([N, K], D)
+    opt.optimal_degrees = degrees
+    opt.feature_means = np.mean(xs, axis=0)
+    opt.feature_stds = np.std(xs, axis=0) + 1e-8
+    opt.qkan_layer = QKANLayer(N=N, K=K, max_degree=D)
+    for d in range(D + 1):                                     # the loop of fit, DegreeOptimizer.py:63-76
+        wv = np.zeros(N * K)
+        for out_idx, connections in enumerate(degrees):
+            for in_idx, degree in enumerate(connections):
+                if degree == d:
+                    wv[out_idx * N + in_idx] = 1.0
+        opt.qkan_layer.mul_step.set_weights(d, wv)
+    W = np.array([opt.qkan_layer.mul_step._weights[d] for d in range(D + 1)])
+    z = (xs - opt.feature_means) / opt.feature_stds
+    with contextlib.redirect_stdout(io.StringIO()):
+        pred = np.stack([opt.qkan_layer.forward(z[i], [W[d] for d in range(D + 1)]) for i in range(len(xs))])
+    np.savez(os.path.join(GOLDEN, "degree_predict.npz"), x=xs, degrees=np.array(degrees), W=W, means=opt.feature_means,
+             stds=opt.feature_stds, pred=pred, shape=np.array([N, K, D]))
+    print("degree_predict: pred range", pred.min(), pred.max())
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@ All arithmetic runs in ``libqkan_b200.so`` (hand-written sm_100a CUDA behind the
 from .layer import ChebyshevStep, LCUStep, MulStep, QKANLayer, SUMStep
 from . import _binding
 from .distributed import FusedGatherQKANLayer, ShardedQKANLayer, shard_bounds
+from .degree_optimizer import DegreeOptimizer
 
-__all__ = ["ChebyshevStep", "MulStep", "LCUStep", "SUMStep", "QKANLayer", "ShardedQKANLayer", "FusedGatherQKANLayer", "shard_bounds"]
+__all__ = ["ChebyshevStep", "MulStep", "LCUStep", "SUMStep", "QKANLayer", "ShardedQKANLayer", "FusedGatherQKANLayer", "shard_bounds", "DegreeOptimizer"]
 __version__ = "0.1.0"

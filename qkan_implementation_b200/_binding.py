@@ -23,6 +23,7 @@ EXPORTS = [
     "qkan_layer_forward_host", "qkan_layer_forward_peers", "qkan_layer_forward_multicast", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals",
     "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version", "qkan_simulate_circuit",
     "qkan_set_last_error",
+    "qkan_cheb_gram_workspace", "qkan_cheb_gram", "qkan_cheb_residuals_ctas", "qkan_cheb_residuals", "qkan_cheb_features",
 ]
 
 
@@ -75,6 +76,11 @@ def lib():
     L.qkan_forward.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
     L.qkan_simulate_circuit.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
     L.qkan_measure_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.qkan_cheb_gram_workspace.argtypes = [i64, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i32)]
+    L.qkan_cheb_gram.argtypes = [vp, vp, i64, i32, i32, vp, vp, i64, vp]
+    L.qkan_cheb_residuals_ctas.argtypes = [ctypes.POINTER(i32)]
+    L.qkan_cheb_residuals.argtypes = [vp, vp, vp, i64, i32, i32, vp, ctypes.c_double, vp, vp, vp, vp]
+    L.qkan_cheb_features.argtypes = [vp, i64, i32, i32, vp, vp]
     L.qkan_last_error.restype = ctypes.c_char_p
     L.qkan_version.argtypes = [ctypes.POINTER(i32)] * 3
     L.qkan_version.restype = None

@@ -1,0 +1,402 @@
+// qkan_degree.cu - SURVEY 8(f) rank 4: the degree-evaluation least squares of the reference's
+// DegreeOptimizer.evaluate_degree (original_degree_optimizer/DegreeOptimizer.py:122-158) on the GPU.
+//
+// The reference builds, for every candidate degree d = 0..D, the design matrix
+//     X_d = [T_0(x) | T_1(x) | ... | T_d(x)],   T_k(x) = cos(k arccos(clip(x, -1, 1)))    (ChebyshevStep.py:32-53)
+// over all n samples and F features, solves min |X_d c - y| with np.linalg.lstsq and scores the fit.  All
+// X_d are column prefixes of X_D, so ONE Gram matrix of the augmented matrix [X_D | y] carries the normal
+// equations of every degree (leading blocks), X_d^T y, sum(y) and y^T y.  Two kernels:
+//   * qkan_cheb_gram_kernel: fused Chebyshev-feature generation + FP64 tensor-core SYRK (mma.sync m8n8k4,
+//     DMMA): a CTA owns one 64 x 64 tile of the upper triangle and one slice of the samples; features are
+//     produced into shared memory from x (recurrence T_{k+1} = 2 x T_k - T_{k-1}) while the next chunk's x
+//     is already in flight; partial tiles are reduced in a fixed order (deterministic, no atomics).
+//     Internally columns are feature-major (f (D+1) + k) so that a 64-column tile reads only ~64 / (D+1)
+//     features of x; the result is written degree-major (k F + f), the reference's np.hstack order.
+//   * qkan_cheb_residual_kernel: the fits' explicit residuals r_d = y - X_d c_d for all d in one pass (one
+//     warp per sample), giving the sums behind the reference's MSE / R^2 (DegreeOptimizer.py:277-312) without
+//     the cancellation of y^T y - 2 c^T g + c^T G c, and X_D^T r_d for one step of iterative refinement.
+// The (D+1) small dense solves run on the host above the C ABI (numpy), as in the reference.
+#include "../../include/qkan_b200.h"
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace {
+
+constexpr int TILE = 64;          // Gram tile edge
+constexpr int KC = 32;            // samples per shared-memory chunk
+constexpr int LD = TILE + 4;      // chunk row stride (doubles): the 16 lanes of a half warp read (k, m) = (0..3, 0..3)
+                                  // -> words k * 68 + m cover 16 different banks
+constexpr int GRAM_THREADS = 128; // 4 warps, each a 32 x 32 quadrant of the tile
+constexpr int MAX_D = 16;
+
+__device__ __forceinline__ double clip_unit(double x) {
+    return x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);       // comparisons keep NaN, like np.clip (ChebyshevStep.py:52)
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// column c' (feature-major, augmented) of sample row: f = c' / (D+1), k = c' % (D+1); column P is y
+struct GramParams {
+    const double* x;       // [n, F]
+    const double* y;       // [n]
+    double* partial;       // [S][n_tiles][TILE * TILE]
+    long long n;
+    int F, D, P;           // P = F (D+1); augmented width P + 1
+    int T;                 // tiles per edge = ceil((P + 1) / TILE)
+    int S;                 // sample slices
+};
+
+// fill one side's chunk: rows = samples s0 .. s0 + KC, columns c0 .. c0 + TILE of the augmented matrix
+template <int MAXI>
+__device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI], int items,
+                                           int f_lo, int nf) {
+    // item = (sample kk, feature slot j): thread t handles items t, t + NT, ...; values were prefetched into xv[]
+    const int D1 = p.D + 1;
+#pragma unroll
+    for (int it = 0; it < MAXI; ++it) {
+        const int item = threadIdx.x + it * GRAM_THREADS;
+        if (it >= items) break;
+        const int kk = item / (nf + 1), j = item - kk * (nf + 1);
+        if (kk >= KC) break;
+        const bool live = s0 + kk < p.n;
+        double* row = dst + kk * LD;
+        if (j == nf) {                                   // the y column (if this tile holds it) and the padding beyond P
+            const int cy = p.P - c0;
+            if (cy >= 0 && cy < TILE) row[cy] = live ? xv[it] : 0.0;
+            for (int c = (cy >= 0 ? cy + 1 : 0); c < TILE; ++c)
+                if (c0 + c > p.P) row[c] = 0.0;
+            continue;
+        }
+        const int f = f_lo + j;
+        const double xc = clip_unit(xv[it]);
+        double t0 = 1.0, t1 = xc;
+        const int cbase = f * D1 - c0;                   // tile column of degree 0 of this feature
+        for (int k = 0; k < D1; ++k) {
+            const double tk = k == 0 ? 1.0 : t1;
+            const int c = cbase + k;
+            if (c >= 0 && c < TILE && f < p.F) row[c] = live ? tk : 0.0;
+            if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+        }
+    }
+}
+
+// MAXI = most (sample, feature) items a thread fills per chunk and side: 32 (64 / (D+1) + 2) / 128
+template <int MAXI>
+__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : 3) qkan_cheb_gram_kernel(const GramParams p) {
+    __shared__ __align__(16) double As[KC * LD];
+    __shared__ __align__(16) double Bs[KC * LD];
+    // upper-triangle tile (ti <= tj) from the linear tile index
+    int ti = 0, rem = blockIdx.x;
+    while (rem >= p.T - ti) { rem -= p.T - ti; ++ti; }
+    const int tj = ti + rem;
+    const bool diag = ti == tj;
+    const int ca = ti * TILE, cb = tj * TILE;
+    const int D1 = p.D + 1;
+    // features touched by each side's 64 columns (+ one pseudo feature slot per sample: y / padding)
+    const int fa_lo = ca / D1, fb_lo = cb / D1;
+    auto nfeat = [&](int c0, int f_lo) {
+        int c_hi = c0 + TILE - 1;
+        if (c_hi > p.P - 1) c_hi = p.P - 1;
+        const int n = c_hi >= c0 ? c_hi / D1 - f_lo + 1 : 0;
+        return n;
+    };
+    const int nfa = nfeat(ca, fa_lo), nfb = nfeat(cb, fb_lo);
+    const int items_a = (KC * (nfa + 1) + GRAM_THREADS - 1) / GRAM_THREADS;
+    const int items_b = diag ? 0 : (KC * (nfb + 1) + GRAM_THREADS - 1) / GRAM_THREADS;
+    double xa[MAXI], xb[MAXI];
+
+    const long long per = (p.n + p.S - 1) / p.S;
+    const long long s_begin = (long long)blockIdx.y * per;
+    long long s_end = s_begin + per;
+    if (s_end > p.n) s_end = p.n;
+
+    auto prefetch = [&](long long s0, double (&xv)[MAXI], int items, int f_lo, int nf) {
+#pragma unroll
+        for (int it = 0; it < MAXI; ++it) {
+            const int item = threadIdx.x + it * GRAM_THREADS;
+            if (it >= items) break;
+            const int kk = item / (nf + 1), j = item - kk * (nf + 1);
+            double v = 0.0;
+            if (kk < KC && s0 + kk < s_end) {
+                if (j == nf) v = p.y[s0 + kk];
+                else if (f_lo + j < p.F) v = p.x[(s0 + kk) * p.F + f_lo + j];
+            }
+            xv[it] = v;
+        }
+    };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;      // the warp's 32 x 32 quadrant
+    const int lr = lane >> 2, lk = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // the chunk loop treats samples beyond s_end as zero rows (live test uses p.n; slices end on s_end)
+    GramParams q = p;
+    q.n = s_end;
+    if (s_begin < s_end) {
+        prefetch(s_begin, xa, items_a, fa_lo, nfa);
+        if (!diag) prefetch(s_begin, xb, items_b, fb_lo, nfb);
+    }
+    for (long long s0 = s_begin; s0 < s_end; s0 += KC) {
+        __syncthreads();                                 // the previous chunk's fragments are consumed
+        fill_chunk<MAXI>(q, As, s0, ca, xa, items_a, fa_lo, nfa);
+        if (!diag) fill_chunk<MAXI>(q, Bs, s0, cb, xb, items_b, fb_lo, nfb);
+        __syncthreads();
+        if (s0 + KC < s_end) {                           // next chunk's x / y: in flight during the MMAs
+            prefetch(s0 + KC, xa, items_a, fa_lo, nfa);
+            if (!diag) prefetch(s0 + KC, xb, items_b, fb_lo, nfb);
+        }
+        const double* Bsrc = diag ? As : Bs;
+#pragma unroll
+        for (int k4 = 0; k4 < KC; k4 += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[(k4 + lk) * LD + wm + i * 8 + lr];      // A[m = lane/4][k = lane%4]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bsrc[(k4 + lk) * LD + wn + j * 8 + lr];    // B[k = lane%4][n = lane/4]
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    // C fragment: (row = lane/4, cols 2 (lane%4) + {0, 1}) of each 8 x 8 block
+    double* out = p.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (TILE * TILE);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = wm + i * 8 + lr, c = wn + j * 8 + 2 * lk;
+            out[r * TILE + c] = acc[i][j][0];
+            out[r * TILE + c + 1] = acc[i][j][1];
+        }
+}
+
+// sum the slices in a fixed order and scatter the tile into the degree-major (P+1) x (P+1) result (both triangles)
+__global__ void qkan_cheb_gram_reduce_kernel(const double* partial, int n_tiles, int S, int T, int F, int D, int P, double* G) {
+    const int tile = blockIdx.x;
+    int ti = 0, rem = tile;
+    while (rem >= T - ti) { rem -= T - ti; ++ti; }
+    const int tj = ti + rem;
+    const int D1 = D + 1;
+    auto to_degree_major = [&](int c) { return c == P ? P : (c % D1) * F + c / D1; };
+    for (int e = threadIdx.x; e < TILE * TILE; e += blockDim.x) {
+        const int r = ti * TILE + e / TILE, c = tj * TILE + e % TILE;
+        if (r > P || c > P) continue;
+        double s = 0.0;
+        for (int q = 0; q < S; ++q) s += partial[((size_t)q * n_tiles + tile) * (TILE * TILE) + e];
+        const int rr = to_degree_major(r), cc = to_degree_major(c);
+        G[(size_t)rr * (P + 1) + cc] = s;
+        G[(size_t)cc * (P + 1) + rr] = s;
+    }
+}
+
+// ---- residual pass: one warp per sample, lanes over features
+// coef [D+1][P] degree-major (zero where the column's degree exceeds d).  Per CTA partial sums:
+//   sums[cta][d][0] = sum r_d^2, [1] = sum w r_d^2;   tail[cta] = {sum (y - ybar)^2, sum w y^2, sum w, sum y}
+//   xtr[cta][d][P]  = X_D^T r_d   (optional)
+constexpr int RES_THREADS = 256;
+
+template <int D1>
+__global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const double* x, const double* y, const double* w, long long n, int F,
+                                                                        const double* coef, double ybar, double* sums,
+                                                                        double* tail, double* xtr) {
+    extern __shared__ double sm[];
+    const int P = F * D1;
+    double* s_xtr = sm;                                  // [D1][P] CTA accumulators of X^T r_d (if requested)
+    double* s_red = sm + (xtr ? (size_t)D1 * P : 0);     // [warps][2 D1 + 4]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = RES_THREADS / 32;
+    if (xtr)
+        for (int i = threadIdx.x; i < D1 * P; i += RES_THREADS) s_xtr[i] = 0.0;
+    __syncthreads();
+    double a_sse[D1], a_wsse[D1];
+#pragma unroll
+    for (int d = 0; d < D1; ++d) a_sse[d] = a_wsse[d] = 0.0;
+    double a_tot = 0.0, a_wyy = 0.0, a_w = 0.0, a_y = 0.0;
+    const long long gw = (long long)blockIdx.x * nwarp + warp, nw = (long long)gridDim.x * nwarp;
+    for (long long s = gw; s < n; s += nw) {
+        double pred[D1];
+#pragma unroll
+        for (int d = 0; d < D1; ++d) pred[d] = 0.0;
+        for (int f = lane; f < F; f += 32) {
+            const double xc = clip_unit(x[s * F + f]);
+            double t0 = 1.0, t1 = xc;
+#pragma unroll
+            for (int k = 0; k < D1; ++k) {
+                const double tk = k == 0 ? 1.0 : t1;
+#pragma unroll
+                for (int d = k; d < D1; ++d) pred[d] = fma(tk, coef[(size_t)d * P + k * F + f], pred[d]);
+                if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < D1; ++d)
+            for (int m = 16; m >= 1; m >>= 1) pred[d] += __shfl_xor_sync(0xffffffffu, pred[d], m);
+        const double yv = y[s], wv = w ? w[s] : 1.0;
+        double r[D1];
+#pragma unroll
+        for (int d = 0; d < D1; ++d) r[d] = yv - pred[d];
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < D1; ++d) { a_sse[d] += r[d] * r[d]; a_wsse[d] += wv * r[d] * r[d]; }
+            a_tot += (yv - ybar) * (yv - ybar);
+            a_wyy += wv * yv * yv;
+            a_w += wv;
+            a_y += yv;
+        }
+        if (xtr) {
+            for (int f = lane; f < F; f += 32) {
+                const double xc = clip_unit(x[s * F + f]);
+                double t0 = 1.0, t1 = xc;
+#pragma unroll
+                for (int k = 0; k < D1; ++k) {
+                    const double tk = k == 0 ? 1.0 : t1;
+#pragma unroll
+                    for (int d = 0; d < D1; ++d) atomicAdd(&s_xtr[(size_t)d * P + k * F + f], tk * r[d]);
+                    if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                }
+            }
+        }
+    }
+    constexpr int Q = 2 * D1 + 4;
+    if (lane == 0) {
+        double* o = s_red + warp * Q;
+#pragma unroll
+        for (int d = 0; d < D1; ++d) { o[2 * d] = a_sse[d]; o[2 * d + 1] = a_wsse[d]; }
+        o[2 * D1] = a_tot; o[2 * D1 + 1] = a_wyy; o[2 * D1 + 2] = a_w; o[2 * D1 + 3] = a_y;
+    }
+    __syncthreads();
+    if (threadIdx.x < Q) {
+        double s = 0.0;
+        for (int wq = 0; wq < nwarp; ++wq) s += s_red[wq * Q + threadIdx.x];
+        if (threadIdx.x < 2 * D1) sums[(size_t)blockIdx.x * 2 * D1 + threadIdx.x] = s;
+        else tail[(size_t)blockIdx.x * 4 + threadIdx.x - 2 * D1] = s;
+    }
+    if (xtr)
+        for (int i = threadIdx.x; i < D1 * P; i += RES_THREADS) xtr[(size_t)blockIdx.x * D1 * P + i] = s_xtr[i];
+}
+
+__global__ void qkan_cheb_features_kernel(const double* x, long long n, int F, int D, double* out) {
+    // out [D+1][n][F]: the reference's transforms[d] (DegreeOptimizer.py:96-119)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * F) return;
+    const double xc = clip_unit(x[i]);
+    double t0 = 1.0, t1 = xc;
+    out[i] = 1.0;
+    for (int k = 1; k <= D; ++k) {
+        out[(size_t)k * n * F + i] = t1;
+        const double t2 = 2.0 * xc * t1 - t0;
+        t0 = t1; t1 = t2;
+    }
+}
+
+int fail(int code, const char* msg) {
+    qkan_set_last_error(msg);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    qkan_set_last_error(buf);
+    return QKAN_ERR_CUDA;
+}
+
+}  // namespace
+
+extern "C" int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes, int* slices) {
+    if (!bytes || n < 0 || F < 1 || D < 0 || D > MAX_D) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram_workspace: bad arguments");
+    const int P = F * (D + 1), T = (P + 1 + TILE - 1) / TILE, n_tiles = T * (T + 1) / 2;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // about four waves of CTAs, at least 8 chunks of samples per slice
+    int S = (4 * 4 * sms + n_tiles - 1) / n_tiles;
+    const long long max_s = n / (8 * KC) > 0 ? n / (8 * KC) : 1;
+    if (S > max_s) S = (int)max_s;
+    if (S < 1) S = 1;
+    *bytes = (int64_t)S * n_tiles * TILE * TILE * (int64_t)sizeof(double);
+    if (slices) *slices = S;
+    return QKAN_OK;
+}
+
+extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F, int D, double* G, void* workspace,
+                              int64_t workspace_bytes, void* cuda_stream) {
+    if (!x || !y || !G || !workspace) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram: null pointer");
+    if (n < 1 || F < 1 || D < 0 || D > MAX_D) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram: need n >= 1, F >= 1, 0 <= D <= 16");
+    int64_t need = 0;
+    int S = 1;
+    int rc = qkan_cheb_gram_workspace(n, F, D, &need, &S);
+    if (rc) return rc;
+    if (workspace_bytes < need) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram: workspace too small (see qkan_cheb_gram_workspace)");
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    GramParams p;
+    p.x = x; p.y = y; p.partial = (double*)workspace; p.n = n; p.F = F; p.D = D; p.P = F * (D + 1);
+    p.T = (p.P + 1 + TILE - 1) / TILE;
+    p.S = S;
+    const int n_tiles = p.T * (p.T + 1) / 2;
+    if (D >= 1) qkan_cheb_gram_kernel<9><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);
+    else qkan_cheb_gram_kernel<17><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");
+    qkan_cheb_gram_reduce_kernel<<<n_tiles, 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_reduce_kernel launch");
+    return QKAN_OK;
+}
+
+extern "C" int qkan_cheb_residuals_ctas(int* ctas) {
+    if (!ctas) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *ctas = 4 * sms;
+    return QKAN_OK;
+}
+
+extern "C" int qkan_cheb_residuals(const double* x, const double* y, const double* w, int64_t n, int F, int D, const double* coef,
+                                   double ybar, double* sums, double* tail, double* xtr, void* cuda_stream) {
+    if (!x || !y || !coef || !sums || !tail) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_residuals: null pointer");
+    if (n < 1 || F < 1 || D < 0 || D > MAX_D) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_residuals: need n >= 1, F >= 1, 0 <= D <= 16");
+    int ctas = 0;
+    qkan_cheb_residuals_ctas(&ctas);
+    const int D1 = D + 1, P = F * D1;
+    const size_t smem = ((xtr ? (size_t)D1 * P : 0) + (size_t)(RES_THREADS / 32) * (2 * D1 + 4)) * sizeof(double);
+    if (smem > 200 * 1024) return fail(QKAN_ERR_UNSUPPORTED, "qkan_cheb_residuals: (D+1)^2 F too large for the refinement accumulators");
+    cudaError_t e = cudaSuccess;
+#define QK_RES_CASE(DD)                                                                                                              \
+    case DD:                                                                                                                         \
+        e = cudaFuncSetAttribute(qkan_cheb_residual_kernel<DD + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e == cudaSuccess)                                                                                                        \
+            qkan_cheb_residual_kernel<DD + 1><<<ctas, RES_THREADS, smem, (cudaStream_t)cuda_stream>>>(x, y, w, n, F, coef, ybar,     \
+                                                                                                   sums, tail, xtr);               \
+        break;
+    switch (D) {
+        QK_RES_CASE(0) QK_RES_CASE(1) QK_RES_CASE(2) QK_RES_CASE(3) QK_RES_CASE(4) QK_RES_CASE(5) QK_RES_CASE(6) QK_RES_CASE(7)
+        QK_RES_CASE(8) QK_RES_CASE(9) QK_RES_CASE(10) QK_RES_CASE(11) QK_RES_CASE(12) QK_RES_CASE(13) QK_RES_CASE(14)
+        QK_RES_CASE(15) QK_RES_CASE(16)
+    }
+#undef QK_RES_CASE
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qkan_cheb_residual_kernel)");
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_residual_kernel launch");
+    return QKAN_OK;
+}
+
+extern "C" int qkan_cheb_features(const double* x, int64_t n, int F, int D, double* out, void* cuda_stream) {
+    if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_features: null pointer");
+    if (n < 0 || F < 1 || D < 0) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_features: bad shape");
+    if (n == 0) return QKAN_OK;
+    const long long tot = (long long)n * F;
+    qkan_cheb_features_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(x, n, F, D, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_features_kernel launch");
+    return QKAN_OK;
+}

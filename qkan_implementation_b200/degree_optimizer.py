@@ -1,0 +1,319 @@
+"""Host mirror of the reference's DegreeOptimizer (original_degree_optimizer/DegreeOptimizer.py) on the B200 path
+(SURVEY 8(f) ranks 3 and 4): same constructor, attributes and method names; `predict` runs the batch through the
+drop-in QKANLayer, `evaluate_degree` runs the Chebyshev-feature least squares on the GPU (csrc/qkan_degree.cu),
+and the QUBO of `optimize_layer` - which is separable per function - is minimised in closed form instead of by
+pyqubo + neal simulated annealing.  There is no CPU fallback: every numeric method needs libqkan_b200.so and a GPU.
+
+Accepted data containers: anything with ``to_numpy()`` (the reference passes polars DataFrames), NumPy arrays and
+torch tensors (CPU or CUDA).
+"""
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _binding as _b
+from .layer import QKANLayer
+
+
+def _as_numpy(a) -> np.ndarray:
+    if hasattr(a, "to_numpy"):
+        a = a.to_numpy()
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a, dtype=np.float64)
+
+
+def _as_device(a, device) -> torch.Tensor:
+    if hasattr(a, "to_numpy"):
+        a = a.to_numpy()
+    if not isinstance(a, torch.Tensor):
+        a = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64)))
+    return a.to(device=device, dtype=torch.float64).contiguous()
+
+
+class ChebyshevLeastSquares:
+    """The GPU side of evaluate_degree: Gram matrix of [T_0(x) | ... | T_D(x) | y] (qkan_cheb_gram), the small
+    minimum-norm solves on the host, explicit residual sums (qkan_cheb_residuals) with one step of iterative
+    refinement."""
+
+    def __init__(self, max_degree: int, device: Optional[int] = None):
+        if not 0 <= max_degree <= 16:
+            raise ValueError("the GPU degree evaluation covers 0 <= max_degree <= 16")
+        if not torch.cuda.is_available():
+            raise RuntimeError("qkan_implementation_b200 needs a CUDA device (no CPU fallback)")
+        self.D = int(max_degree)
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.last = {}
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def gram(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        n, F = x.shape
+        P = F * (self.D + 1)
+        need, slices = ctypes.c_int64(), ctypes.c_int()
+        with torch.cuda.device(self.device):
+            _b.check(_b.lib().qkan_cheb_gram_workspace(n, F, self.D, ctypes.byref(need), ctypes.byref(slices)))
+            ws = torch.empty(max(1, need.value // 8), dtype=torch.float64, device=self.device)
+            G = torch.empty((P + 1, P + 1), dtype=torch.float64, device=self.device)
+            _b.check(_b.lib().qkan_cheb_gram(x.data_ptr(), y.data_ptr(), n, F, self.D, G.data_ptr(), ws.data_ptr(),
+                                             need.value, self._stream()))
+        return G
+
+    def residual_sums(self, x, y, w, coef: np.ndarray, ybar: float, want_xtr: bool):
+        n, F = x.shape
+        D1, P = self.D + 1, F * (self.D + 1)
+        ctas = ctypes.c_int()
+        _b.check(_b.lib().qkan_cheb_residuals_ctas(ctypes.byref(ctas)))
+        c = ctas.value
+        with torch.cuda.device(self.device):
+            cd = torch.from_numpy(np.ascontiguousarray(coef)).to(self.device)
+            sums = torch.empty((c, D1, 2), dtype=torch.float64, device=self.device)
+            tail = torch.empty((c, 4), dtype=torch.float64, device=self.device)
+            xtr = torch.empty((c, D1, P), dtype=torch.float64, device=self.device) if want_xtr else None
+            _b.check(_b.lib().qkan_cheb_residuals(x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None, n, F,
+                                                  self.D, cd.data_ptr(), float(ybar), sums.data_ptr(), tail.data_ptr(),
+                                                  xtr.data_ptr() if want_xtr else None, self._stream()))
+            # CTA partials are added in CTA order (deterministic)
+            s = sums.cpu().numpy().sum(axis=0)
+            t = tail.cpu().numpy().sum(axis=0)
+            xr = xtr.sum(dim=0).cpu().numpy() if want_xtr else None
+        return s, t, xr
+
+    @staticmethod
+    def _pinv_solve(A: np.ndarray, b: np.ndarray, n: int) -> np.ndarray:
+        """Minimum-norm least-squares solution from the normal equations (what np.linalg.lstsq returns for the
+        rank-deficient X_d: the T_0 columns of all features are identical).  Eigenvalues below the larger of lstsq's
+        own cut-off (rcond = eps max(n, P) on singular values) and the resolution of a Gram matrix are dropped."""
+        lam, V = np.linalg.eigh(A)
+        eps = np.finfo(np.float64).eps
+        P = len(b)
+        cut = lam[-1] * max((eps * max(n, P)) ** 2, 64.0 * P * eps)
+        keep = lam > cut
+        Vk = V[:, keep]
+        return Vk @ ((Vk.T @ b) / lam[keep])
+
+    def solve(self, x, y, weights=None, refine: int = 1):
+        """x [n, F], y [n], weights [n] or None -> (scores [D+1] = MSE, comp_r2 [D+1]) as evaluate_degree."""
+        x = _as_device(x, self.device)
+        y = _as_device(y, self.device).reshape(-1)
+        w = _as_device(weights, self.device).reshape(-1) if weights is not None else None
+        n, F = x.shape
+        if y.shape[0] != n or (w is not None and w.shape[0] != n):
+            raise ValueError("x, y and weights must have the same number of rows")
+        D1, P = self.D + 1, F * (self.D + 1)
+        G = self.gram(x, y).cpu().numpy()
+        ybar = G[0, P] / n                                   # column 0 = T_0 of feature 0 = ones
+        coef = np.zeros((D1, P))
+        for d in range(D1):
+            Pd = F * (d + 1)
+            coef[d, :Pd] = self._pinv_solve(G[:Pd, :Pd], G[:Pd, P], n)
+        for _ in range(max(0, refine)):                      # iterative refinement on the explicit residuals
+            _, _, xr = self.residual_sums(x, y, w, coef, ybar, True)
+            for d in range(D1):
+                Pd = F * (d + 1)
+                coef[d, :Pd] += self._pinv_solve(G[:Pd, :Pd], xr[d, :Pd], n)
+        s, t, _ = self.residual_sums(x, y, w, coef, ybar, False)
+        scores, comp_r2 = np.zeros(D1), np.zeros(D1)
+        eps = np.finfo(float).eps
+        for d in range(D1):
+            sse, wsse = s[d]
+            if w is not None:                                # DegreeOptimizer.py:291-298 (names as in the reference)
+                mse, ss_tot, ss_res = wsse / t[2], wsse, t[1]
+            else:                                            # :293-302
+                mse, ss_tot, ss_res = sse / n, t[0], sse
+            scores[d] = mse
+            comp_r2[d] = 0.0 if ss_tot < eps else 1 - ss_tot / ss_res      # :305-309
+        self.last = {"coef": coef, "gram": G, "ybar": ybar}
+        return scores, comp_r2
+
+    def features(self, x) -> np.ndarray:
+        """[D+1, n, F]: T_d(clip(x)) (DegreeOptimizer._compute_transforms, :96-119)."""
+        xd = _as_device(x, self.device)
+        n, F = xd.shape
+        out = torch.empty((self.D + 1, n, F), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _b.check(_b.lib().qkan_cheb_features(xd.data_ptr(), n, F, self.D, out.data_ptr(), self._stream()))
+        return out.cpu().numpy()
+
+
+class DegreeOptimizer:
+    """original_degree_optimizer/DegreeOptimizer.py:13-40 (constructor arguments, defaults and attributes)."""
+
+    def __init__(self, network_shape: List[int], max_degree: int, complexity_weight: float = 0.1,
+                 significance_threshold: float = 0.05):
+        self.fold_caches = {}                                # BaseOptimizer.py:8-10
+        self.network_shape = network_shape
+        self.num_layers = len(network_shape) - 1
+        self.max_degree = max_degree
+        self.complexity_weight = complexity_weight
+        self.significance_threshold = significance_threshold
+        self.transform_cache = {}
+        self.degree_scores = {}
+        self.data_same = True
+        self.optimal_degrees = None
+        self.coefficients = None
+        self.feature_means = None
+        self.feature_stds = None
+        self.qkan_layer: Optional[QKANLayer] = None
+        self._lsq: Optional[ChebyshevLeastSquares] = None
+
+    def _engine(self) -> ChebyshevLeastSquares:
+        if self._lsq is None or self._lsq.D != self.max_degree:
+            self._lsq = ChebyshevLeastSquares(self.max_degree)
+        return self._lsq
+
+    # ------------------------------------------------------------------ fit / predict (DegreeOptimizer.py:42-95)
+    def fit(self, x_data, y_data, weights=None) -> None:
+        self.optimal_degrees = self.optimize_layer(layer_idx=0, x_data=x_data, y_data=y_data, weights=weights)
+        feature_data = _as_numpy(x_data)
+        self.feature_means = np.mean(feature_data, axis=0)
+        self.feature_stds = np.std(feature_data, axis=0) + 1e-8
+        self._build_layer()
+
+    def _build_layer(self) -> None:
+        N, K = self.network_shape[0], self.network_shape[1]
+        self.qkan_layer = QKANLayer(N=N, K=K, max_degree=self.max_degree)
+        for d in range(self.max_degree + 1):                 # :63-76
+            w = np.zeros(N * K)
+            for out_idx, connections in enumerate(self.optimal_degrees):
+                for in_idx, degree in enumerate(connections):
+                    if degree == d:
+                        w[out_idx * N + in_idx] = 1.0
+            self.qkan_layer.mul_step.set_weights(d, w)
+
+    def predict(self, x_data) -> np.ndarray:
+        """:78-95, for the whole batch in one launch (the reference's 2-D call raises in MulStep.py:62-66);
+        z-scored inputs beyond [-1, 1] are clipped by the layer, with the reference's warning."""
+        if self.qkan_layer is None:
+            raise RuntimeError('Not fitted yet')
+        feature_data = _as_numpy(x_data)
+        normalized_data = (feature_data - self.feature_means) / self.feature_stds
+        weights = [self.qkan_layer.mul_step._weights[d] for d in range(self.max_degree + 1)]
+        return self.qkan_layer.forward(x=normalized_data, weights=weights, verbose=False)
+
+    # ------------------------------------------------------------------ degree evaluation (:96-181)
+    def _compute_transforms(self, feature_data: np.ndarray) -> Dict[int, np.ndarray]:
+        t = self._engine().features(feature_data)
+        return {d: t[d] for d in range(self.max_degree + 1)}
+
+    def evaluate_degree(self, x_data, y_data, weights=None) -> Tuple[np.ndarray, np.ndarray]:
+        """:122-158: (scores = MSE per degree, comp_r2 = the reference's R^2 per degree)."""
+        cache_key = str(getattr(x_data, "schema", None))
+        if cache_key in self.degree_scores and self.data_same:
+            print("Using cached degree scores...")
+            return self.degree_scores[cache_key]
+        x = x_data.to_numpy() if hasattr(x_data, "to_numpy") else x_data
+        scores, comp_r2 = self._engine().solve(x, y_data, weights)
+        for d in range(self.max_degree + 1):
+            print(f"\nDegree {d}:")
+            print(f"MSE: {scores[d]:.8f}")
+            print(f"R²:  {comp_r2[d]:.8f}")
+        return scores, comp_r2
+
+    def is_degree_definitive(self, scores: np.ndarray) -> Tuple[bool, int]:
+        """:159-181."""
+        best_degree = int(np.argmin(scores))
+        best_score = float(scores[best_degree])
+        is_definitive = True
+        for d in range(len(scores)):
+            if d != best_degree:
+                score = float(scores[d])
+                relative_improvement = (score - best_score) / (score + 1e-10)
+                if relative_improvement < self.significance_threshold:
+                    is_definitive = False
+                    break
+        return is_definitive, best_degree
+
+    def optimize_layer(self, layer_idx: int, x_data, y_data, weights, num_reads: int = 1000) -> List[List[int]]:
+        """:183-253.  The reference compiles a QUBO and samples it with neal; its objective is a sum over functions of
+        sum_d a_d q[i, d] + 10 (sum_d q[i, d] - 1)^2 with the same a_d for every function, so the ground state is
+        one-hot at argmin_d a_d for every function - returned here directly (`num_reads` is unused)."""
+        input_dim = self.network_shape[layer_idx]
+        output_dim = self.network_shape[layer_idx + 1]
+        scores, _ = self.evaluate_degree(x_data, y_data, weights)
+        is_definitive, definitive_degree = self.is_degree_definitive(scores)
+        if is_definitive:                                    # :214-219
+            best = definitive_degree
+        else:                                                # :221-225
+            a = [-(scores[d] - scores[d - 1] if d > 0 else scores[d]) + self.complexity_weight * (d ** 2)
+                 for d in range(self.max_degree + 1)]
+            best = int(np.argmin(a))
+        return [[best for _ in range(input_dim)] for _ in range(output_dim)]
+
+    def optimize_network(self, training_data: Dict[str, np.ndarray], num_reads: int = 1000) -> List[List[List[int]]]:
+        """:255-275."""
+        return [self.optimize_layer(layer_idx=layer, x_data=training_data[f'layer_{layer}_input'],
+                                    y_data=training_data[f'layer_{layer}_output'], weights=None, num_reads=num_reads)
+                for layer in range(self.num_layers)]
+
+    def _compute_metrics(self, y_true, y_pred, weights=None) -> Dict[str, float]:
+        """:277-312 for explicit predictions (host arithmetic on the caller's arrays, as in the reference)."""
+        y_true = np.asarray(y_true).reshape(-1, 1)
+        y_pred = np.asarray(y_pred).reshape(-1, 1)
+        squared_errors = (y_true - y_pred) ** 2
+        if weights is not None:
+            weights = np.asarray(weights).reshape(-1, 1)
+            mse = np.average(squared_errors, weights=weights)
+            ss_tot = np.sum(weights * squared_errors)
+            ss_res = np.sum(weights * y_true ** 2)
+        else:
+            mse = np.mean(squared_errors)
+            ss_tot = np.sum((y_true - np.mean(y_true)) ** 2)
+            ss_res = np.sum(squared_errors)
+        if ss_tot < np.finfo(float).eps:
+            print(f"Warning: Total sum of squares ({ss_tot}) near zero - data might be over-normalized")
+            r2 = 0.0
+        else:
+            r2 = 1 - ss_tot / ss_res
+        return {'mse': float(mse), 'r2': float(r2)}
+
+    # ------------------------------------------------------------------ state (:313-375)
+    def save_state(self, filename: str, query_params: Dict = None) -> None:
+        if query_params is None:
+            query_params = {'n_rows': 100000,
+                            'columns': ['date_id', 'responder_6', 'weight'] + [f'feature_{i:02d}' for i in range(79)],
+                            'sort_by': 'date_id'}
+        qkan_params = None
+        if self.qkan_layer is not None:
+            qkan_params = {'weights': [self.qkan_layer.mul_step._weights[d].copy() for d in range(self.max_degree + 1)],
+                           'feature_means': self.feature_means.copy(), 'feature_stds': self.feature_stds.copy(),
+                           'optimal_degrees': list(self.optimal_degrees)}
+        state = {'network_shape': self.network_shape, 'max_degree': self.max_degree,
+                 'complexity_weight': self.complexity_weight, 'significance_threshold': self.significance_threshold,
+                 'transform_cache': self.transform_cache, 'degree_scores': self.degree_scores,
+                 'query_params': query_params, 'qkan_params': qkan_params}
+        np.save(filename, state)
+
+    def load_state(self, filename: str, current_query_params: dict) -> None:
+        state = np.load(filename, allow_pickle=True).item()
+        self.network_shape = state['network_shape']
+        self.num_layers = len(self.network_shape) - 1
+        self.max_degree = state['max_degree']
+        self.complexity_weight = state['complexity_weight']
+        self.significance_threshold = state['significance_threshold']
+        if state['qkan_params'] is not None:
+            qp = state['qkan_params']
+            self.feature_means = qp['feature_means']
+            self.feature_stds = qp['feature_stds']
+            self.optimal_degrees = qp['optimal_degrees']
+            N, K = self.network_shape[0], self.network_shape[1]
+            self.qkan_layer = QKANLayer(N=N, K=K, max_degree=self.max_degree)
+            for d, weights in enumerate(qp['weights']):
+                self.qkan_layer.mul_step.set_weights(d, weights)
+        if self._validate_query(state['query_params'], current_query_params):
+            print("Loading cached computations")
+            self.transform_cache = state['transform_cache']
+            self.degree_scores = state['degree_scores']
+        else:
+            print("Query changed, clearing caches")
+            self.data_same = False
+            self.transform_cache = {}
+            self.degree_scores = {}
+
+    def _validate_query(self, saved_params: dict, current_query_params: dict) -> bool:
+        return (saved_params['n_rows'] == current_query_params['n_rows'] and
+                saved_params['columns'] == current_query_params['columns'] and
+                saved_params['sort_by'] == current_query_params['sort_by'])

@@ -26,8 +26,9 @@ namespace {
 
 constexpr int TILE = 64;          // Gram tile edge
 constexpr int KC = 32;            // samples per shared-memory chunk
-constexpr int LD = TILE + 4;      // chunk row stride (doubles): the 16 lanes of a half warp read (k, m) = (0..3, 0..3)
-                                  // -> words k * 68 + m cover 16 different banks
+constexpr int LDK = KC + 4;       // shared-memory chunks are [column][sample] with 36 doubles per column: the 16 lanes of a
+                                  // half warp read fragments (m, k) = (0..3, 0..3) -> words 36 m + k, 16 different banks, and
+                                  // the producers write one column for 32 consecutive samples -> consecutive banks
 constexpr int GRAM_THREADS = 128; // 4 warps, each a 32 x 32 quadrant of the tile
 constexpr int MAX_D = 16;
 
@@ -56,21 +57,20 @@ struct GramParams {
 template <int MAXI>
 __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI], int items,
                                            int f_lo, int nf) {
-    // item = (sample kk, feature slot j): thread t handles items t, t + NT, ...; values were prefetched into xv[]
+    // item = (feature slot j, sample kk) with kk = t % 32 fastest: thread t handles slots t / 32, t / 32 + 4, ...;
+    // the values were prefetched into xv[]
     const int D1 = p.D + 1;
+    const int kk = threadIdx.x & (KC - 1);
+    const bool live = s0 + kk < p.n;
 #pragma unroll
     for (int it = 0; it < MAXI; ++it) {
-        const int item = threadIdx.x + it * GRAM_THREADS;
-        if (it >= items) break;
-        const int kk = item / (nf + 1), j = item - kk * (nf + 1);
-        if (kk >= KC) break;
-        const bool live = s0 + kk < p.n;
-        double* row = dst + kk * LD;
+        const int j = (threadIdx.x >> 5) + it * (GRAM_THREADS / KC);
+        if (j > nf) break;
         if (j == nf) {                                   // the y column (if this tile holds it) and the padding beyond P
             const int cy = p.P - c0;
-            if (cy >= 0 && cy < TILE) row[cy] = live ? xv[it] : 0.0;
+            if (cy >= 0 && cy < TILE) dst[cy * LDK + kk] = live ? xv[it] : 0.0;
             for (int c = (cy >= 0 ? cy + 1 : 0); c < TILE; ++c)
-                if (c0 + c > p.P) row[c] = 0.0;
+                if (c0 + c > p.P) dst[c * LDK + kk] = 0.0;
             continue;
         }
         const int f = f_lo + j;
@@ -80,17 +80,17 @@ __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, lon
         for (int k = 0; k < D1; ++k) {
             const double tk = k == 0 ? 1.0 : t1;
             const int c = cbase + k;
-            if (c >= 0 && c < TILE && f < p.F) row[c] = live ? tk : 0.0;
+            if (c >= 0 && c < TILE && f < p.F) dst[c * LDK + kk] = live ? tk : 0.0;
             if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
         }
     }
 }
 
-// MAXI = most (sample, feature) items a thread fills per chunk and side: 32 (64 / (D+1) + 2) / 128
+// MAXI = most feature slots a thread fills per chunk and side: (64 / (D+1) + 2 features + the y slot) / 4
 template <int MAXI>
-__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : 3) qkan_cheb_gram_kernel(const GramParams p) {
-    __shared__ __align__(16) double As[KC * LD];
-    __shared__ __align__(16) double Bs[KC * LD];
+__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
+    __shared__ __align__(16) double As[TILE * LDK];
+    __shared__ __align__(16) double Bs[TILE * LDK];
     // upper-triangle tile (ti <= tj) from the linear tile index
     int ti = 0, rem = blockIdx.x;
     while (rem >= p.T - ti) { rem -= p.T - ti; ++ti; }
@@ -107,8 +107,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : 3) qkan_cheb_gram
         return n;
     };
     const int nfa = nfeat(ca, fa_lo), nfb = nfeat(cb, fb_lo);
-    const int items_a = (KC * (nfa + 1) + GRAM_THREADS - 1) / GRAM_THREADS;
-    const int items_b = diag ? 0 : (KC * (nfb + 1) + GRAM_THREADS - 1) / GRAM_THREADS;
+    const int items_a = 0, items_b = 0;                  // (slot counts follow from nfa / nfb)
     double xa[MAXI], xb[MAXI];
 
     const long long per = (p.n + p.S - 1) / p.S;
@@ -116,14 +115,14 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : 3) qkan_cheb_gram
     long long s_end = s_begin + per;
     if (s_end > p.n) s_end = p.n;
 
-    auto prefetch = [&](long long s0, double (&xv)[MAXI], int items, int f_lo, int nf) {
+    auto prefetch = [&](long long s0, double (&xv)[MAXI], int, int f_lo, int nf) {
+        const int kk = threadIdx.x & (KC - 1);
 #pragma unroll
         for (int it = 0; it < MAXI; ++it) {
-            const int item = threadIdx.x + it * GRAM_THREADS;
-            if (it >= items) break;
-            const int kk = item / (nf + 1), j = item - kk * (nf + 1);
+            const int j = (threadIdx.x >> 5) + it * (GRAM_THREADS / KC);
+            if (j > nf) break;
             double v = 0.0;
-            if (kk < KC && s0 + kk < s_end) {
+            if (s0 + kk < s_end) {
                 if (j == nf) v = p.y[s0 + kk];
                 else if (f_lo + j < p.F) v = p.x[(s0 + kk) * p.F + f_lo + j];
             }
@@ -161,9 +160,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : 3) qkan_cheb_gram
         for (int k4 = 0; k4 < KC; k4 += 4) {
             double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[(k4 + lk) * LD + wm + i * 8 + lr];      // A[m = lane/4][k = lane%4]
+            for (int i = 0; i < 4; ++i) a[i] = As[(wm + i * 8 + lr) * LDK + k4 + lk];      // A[m = lane/4][k = lane%4]
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bsrc[(k4 + lk) * LD + wn + j * 8 + lr];    // B[k = lane%4][n = lane/4]
+            for (int j = 0; j < 4; ++j) b[j] = Bsrc[(wn + j * 8 + lr) * LDK + k4 + lk];    // B[k = lane%4][n = lane/4]
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -343,8 +342,9 @@ extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F
     p.T = (p.P + 1 + TILE - 1) / TILE;
     p.S = S;
     const int n_tiles = p.T * (p.T + 1) / 2;
-    if (D >= 1) qkan_cheb_gram_kernel<9><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);
-    else qkan_cheb_gram_kernel<17><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);
+    if (D >= 3) qkan_cheb_gram_kernel<5><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);        // <= 18 slots per side
+    else if (D >= 1) qkan_cheb_gram_kernel<9><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);   // <= 34
+    else qkan_cheb_gram_kernel<17><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);              // 65
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");
     qkan_cheb_gram_reduce_kernel<<<n_tiles, 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);

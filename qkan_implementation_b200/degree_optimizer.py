@@ -38,7 +38,11 @@ class ChebyshevLeastSquares:
     minimum-norm solves on the host, explicit residual sums (qkan_cheb_residuals) with one step of iterative
     refinement."""
 
-    def __init__(self, max_degree: int, device: Optional[int] = None):
+    def __init__(self, max_degree: int, device: Optional[int] = None, group=None):
+        """group: a torch.distributed process group (one process per GPU, NCCL).  Each rank then passes ITS rows to
+        solve(); the Gram matrices and the residual sums of the ranks add up, so the only exchange is one all-reduce
+        of (P+1)^2 doubles and one of a few hundred - every rank returns the scores of the whole data set."""
+        self.group = group
         if not 0 <= max_degree <= 16:
             raise ValueError("the GPU degree evaluation covers 0 <= max_degree <= 16")
         if not torch.cuda.is_available():
@@ -76,11 +80,19 @@ class ChebyshevLeastSquares:
             _b.check(_b.lib().qkan_cheb_residuals(x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None, n, F,
                                                   self.D, cd.data_ptr(), float(ybar), sums.data_ptr(), tail.data_ptr(),
                                                   xtr.data_ptr() if want_xtr else None, self._stream()))
-            # CTA partials are added in CTA order (deterministic)
-            s = sums.cpu().numpy().sum(axis=0)
-            t = tail.cpu().numpy().sum(axis=0)
-            xr = xtr.sum(dim=0).cpu().numpy() if want_xtr else None
-        return s, t, xr
+            # CTA partials are added in CTA order (deterministic), then the ranks' sums
+            s = sums.sum(dim=0)
+            t = tail.sum(dim=0)
+            xr = xtr.sum(dim=0) if want_xtr else None
+            if self.group is not None:
+                import torch.distributed as dist
+                packed = torch.cat([s.reshape(-1), t.reshape(-1)] + ([xr.reshape(-1)] if want_xtr else []))
+                dist.all_reduce(packed, group=self.group)
+                s = packed[:s.numel()].reshape(s.shape)
+                t = packed[s.numel():s.numel() + t.numel()].reshape(t.shape)
+                if want_xtr:
+                    xr = packed[s.numel() + t.numel():].reshape(xr.shape)
+        return s.cpu().numpy(), t.cpu().numpy(), (xr.cpu().numpy() if want_xtr else None)
 
     @staticmethod
     def _pinv_solve(A: np.ndarray, b: np.ndarray, n: int) -> np.ndarray:
@@ -104,8 +116,15 @@ class ChebyshevLeastSquares:
         if y.shape[0] != n or (w is not None and w.shape[0] != n):
             raise ValueError("x, y and weights must have the same number of rows")
         D1, P = self.D + 1, F * (self.D + 1)
-        G = self.gram(x, y).cpu().numpy()
-        ybar = G[0, P] / n                                   # column 0 = T_0 of feature 0 = ones
+        Gd = self.gram(x, y)
+        n_all = n
+        if self.group is not None:                           # rows are sharded over the ranks: Gram matrices add
+            import torch.distributed as dist
+            dist.all_reduce(Gd, group=self.group)
+            n_all = int(round(float(Gd[0, 0].item())))       # G[0, 0] = sum of T_0^2 = number of rows
+        G = Gd.cpu().numpy()
+        ybar = G[0, P] / n_all                               # column 0 = T_0 of feature 0 = ones
+        n_local, n = n, n_all
         coef = np.zeros((D1, P))
         for d in range(D1):
             Pd = F * (d + 1)
@@ -126,7 +145,7 @@ class ChebyshevLeastSquares:
                 mse, ss_tot, ss_res = sse / n, t[0], sse
             scores[d] = mse
             comp_r2[d] = 0.0 if ss_tot < eps else 1 - ss_tot / ss_res      # :305-309
-        self.last = {"coef": coef, "gram": G, "ybar": ybar}
+        self.last = {"coef": coef, "gram": G, "ybar": ybar, "rows": n, "rows_local": n_local}
         return scores, comp_r2
 
     def features(self, x) -> np.ndarray:

@@ -110,7 +110,7 @@ WINDOW_CTAS = ((256, 4), (256, 3))   # (NT, MINB) of the window kernels (wide in
 def window_instances():
     out = []   # (group, amp, NT, MINB, DT)
     for amp in ("c128", "c64", "r64"):
-        for dt in range(2, DT_MAX + 1):
+        for dt in range(1, DT_MAX + 1):
             for (nt, minb) in WINDOW_CTAS:
                 out.append((f"block_{amp}_d{dt}", amp, nt, minb, dt))
     return out

@@ -294,7 +294,7 @@ QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], co
 #ifndef QKAN_TAN_FORM
 #define QKAN_TAN_FORM 1
 #endif
-constexpr int TAN_MIN_DT = 2;        // D = 1 has no full pass to save; its pre-pass would only get dearer
+constexpr int TAN_MIN_DT = 1;        // D = 1: no full pass to save, but the pruned pass + SELECT are 12 instead of 14 instructions
 // U = 1 only: the U = 4 kernels serve wide input rows, where the cs tile (24 instead of 16 bytes per input
 // element) already limits the resident warps (measured on N784 K10 D5: 3.97 -> 2.96 M samples/s with triples)
 constexpr bool use_tan_form(int mode, int dt, int U) { return QKAN_TAN_FORM && mode == 0 && dt >= TAN_MIN_DT && U == 1; }

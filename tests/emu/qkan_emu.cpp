@@ -113,7 +113,7 @@ template <class A, typename R, int U, int DT> struct TanRun {
         else TanRun<A, R, U, DT - 1>::go(D, init, t, al, be, cw, sw, acc);
     }
 };
-template <class A, typename R, int U> struct TanRun<A, R, U, 1> {
+template <class A, typename R, int U> struct TanRun<A, R, U, 0> {
     static void go(int, const A (&)[4], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], A&) {}
 };
 

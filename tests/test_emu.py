@@ -58,7 +58,7 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
         x[2, :4] = [np.sqrt(0.5), -np.sqrt(0.5), 1e-300, -1.0]      # the quarter-turn boundary, a tiny and a unit input
     W = rng.uniform(-1, 1, (D + 1, N * K))
     spec = o.circuit_spec(N, K, D)
-    tan_ok = 2 <= D <= 16            # scaled-rotation form of the degree-specialised kernels (use_tan_form)
+    tan_ok = 1 <= D <= 16            # scaled-rotation form of the degree-specialised kernels (use_tan_form)
     cases = [(0, 0, 0, 1e-14), (0, 1, 0, 1e-14), (1, 0, 0, 1e-5), (2, 0, 0, 1e-14)]
     if tan_ok:
         cases += [(0, 0, 1, 1e-14), (1, 0, 1, 1e-5), (2, 0, 1, 1e-14)]

@@ -82,6 +82,7 @@ BLOCK_MINB = {
     (2, 1, 256): 3, (2, 1, 128): 6,
     (1, 1, 256): 4, (1, 1, 128): 8, (1, 1, 64): 16, (1, 1, 32): 32,
     (1, 2, 256): 3, (1, 2, 128): 5,
+    (1, 4, 256): 2, (1, 4, 128): 4,      # tuning variants (QKAN_BLOCK_TUNE=1:128:3:4): four samples per lane
 }
 DT_MAX = 16     # compile-time degree specialisations (compat mode): D = 1 .. DT_MAX
 SU2_DT_MAX = 8  # two samples per lane only pay off for shallow sequences
@@ -92,13 +93,13 @@ def block_instances():
     for amp in ("c128", "c64", "r64"):
         for mode in (0, 1):
             for (U, SU, NT), minb in BLOCK_MINB.items():
-                if U == 2 and amp != "c128":
-                    continue          # U = 2 is only reachable through the tuning override
+                if (U == 2 and amp != "c128") or SU == 4:
+                    continue          # U = 2 is only reachable through the tuning override; SU = 4 only degree-specialised
                 out.append((f"block_{amp}_m{mode}", amp, U, SU, mode, NT, minb, 0, 1))
         # degree-specialised kernels: compat mode, CTA sizes 256 / 128
         for dt in range(1, DT_MAX + 1):
             for (U, SU, NT), minb in BLOCK_MINB.items():
-                if NT not in (256, 128) or U == 2 or (SU == 2 and dt > SU2_DT_MAX):
+                if NT not in (256, 128) or U == 2 or (SU == 2 and dt > SU2_DT_MAX) or (SU == 4 and (dt > 4 or amp != "c128")):
                     continue
                 out.append((f"block_{amp}_d{dt}", amp, U, SU, 0, NT, minb, dt, 1))
     return out

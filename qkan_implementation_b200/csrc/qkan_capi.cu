@@ -76,6 +76,8 @@ struct qkan_layer {
     int64_t cap_x = 0, cap_out = 0, cap_amps = 0;
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
+    cudaEvent_t ev_w = nullptr;               // recorded after the table build of set_weights: the host path's own
+                                              // (non-blocking) streams wait on it, whatever stream the caller used
 };
 
 static size_t amp_real_size(int dtype) { return dtype == QKAN_COMPLEX64 ? 4 : 8; }
@@ -241,6 +243,7 @@ extern "C" void qkan_layer_destroy(qkan_layer* l) {
         if (l->ev_in[i]) cudaEventDestroy(l->ev_in[i]);
         if (l->ev_k[i]) cudaEventDestroy(l->ev_k[i]);
     }
+    if (l->ev_w) cudaEventDestroy(l->ev_w);
     delete l;
 }
 
@@ -290,6 +293,8 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
             return fail(QKAN_ERR_WEIGHT_RANGE, "Weight magnitudes must be <= 1 for unitarity");   // MulStep.py:37
         }
     }
+    if (!l->ev_w) CU(cudaEventCreateWithFlags(&l->ev_w, cudaEventDisableTiming));
+    CU(cudaEventRecord(l->ev_w, stream));
     l->weights_set = true;
     return QKAN_OK;
 }
@@ -421,6 +426,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
                 int rc0 = ensure_host_path(l, 0, false);
                 if (rc0) return rc0;
             }
+            if (l->ev_w) CU(cudaStreamWaitEvent(l->s_k, l->ev_w, 0));
             int rc = launch_on(l, (const double*)dx, B, (double*)dout, damps, l->s_k);
             if (rc) return rc;
             CU(cudaStreamSynchronize(l->s_k));
@@ -429,6 +435,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     }
     int rc = ensure_host_path(l, B, amps != nullptr);
     if (rc) return rc;
+    if (l->ev_w) CU(cudaStreamWaitEvent(l->s_k, l->ev_w, 0));
     // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile
     // ~16 MiB of traffic per chunk: 4 chunks for 1M x (4 in + 4 out) doubles measured best on B200 / PCIe 5
     // (profiles/r01_e2e_chunks.txt): fewer chunks expose fill / drain, more add launch and copy overhead

@@ -160,6 +160,8 @@ int qkan_cheb_features(const double* x, int64_t n, int F, int D, double* out, vo
 /* Measured peaks used as roofline denominators: dependent-free FMA chains on every SM.
  * fp64 != 0: DFMA, else FFMA.  Returns TFLOP/s (2 flops per FMA). */
 int qkan_measure_fma_peak(int device, int fp64, double* tflops);
+/* FP64 tensor-core peak: independent mma.sync.m8n8k4.f64 (DMMA) chains on every SM.  TFLOP/s. */
+int qkan_measure_dmma_peak(int device, double* tflops);
 
 const char* qkan_last_error(void);
 int qkan_set_last_error(const char* msg);   /* internal: lets the other translation units report */

@@ -23,7 +23,7 @@ EXPORTS = [
     "qkan_layer_forward_host", "qkan_layer_forward_peers", "qkan_layer_forward_multicast", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals",
     "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version", "qkan_simulate_circuit",
     "qkan_set_last_error",
-    "qkan_cheb_gram_workspace", "qkan_cheb_gram", "qkan_cheb_residuals_ctas", "qkan_cheb_residuals", "qkan_cheb_features",
+    "qkan_measure_dmma_peak", "qkan_cheb_gram_workspace", "qkan_cheb_gram", "qkan_cheb_residuals_ctas", "qkan_cheb_residuals", "qkan_cheb_features",
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.qkan_forward.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp]
     L.qkan_simulate_circuit.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
     L.qkan_measure_fma_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.qkan_measure_dmma_peak.argtypes = [i32, ctypes.POINTER(ctypes.c_double)]
     L.qkan_cheb_gram_workspace.argtypes = [i64, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i32)]
     L.qkan_cheb_gram.argtypes = [vp, vp, i64, i32, i32, vp, vp, i64, vp]
     L.qkan_cheb_residuals_ctas.argtypes = [ctypes.POINTER(i32)]
@@ -91,6 +92,12 @@ def lib():
 def check(rc: int):
     if rc != QKAN_OK:
         raise QkanError(rc, lib().qkan_last_error().decode())
+
+
+def measure_dmma_peak(device: int = 0) -> float:
+    v = ctypes.c_double()
+    check(lib().qkan_measure_dmma_peak(device, ctypes.byref(v)))
+    return v.value
 
 
 def measure_fma_peak(device: int = 0, fp64: bool = True) -> float:

@@ -36,18 +36,15 @@ struct BlockLayout {
     double efficiency;          // live block slots / issued block slots
 };
 
-// cs row stride (entries).  One LDS phase serves 128 bytes = P lanes (P = 8 for 16-byte pairs, 16 for 8-byte
-// words, 32 for 4-byte words); with G < P lanes per sample a phase spans P / G consecutive sample rows, and
-// the lanes of a row read G different entries, so the rows must start G entries apart modulo P:
-// row stride = mult * NP = G (mod P), where mult = entries-worth of words per row entry (1 for the
-// (cos, sin) pair rows, 3 for the three word rows t | alpha | beta of the scaled-rotation form; 3 is
-// coprime to P, so a solution exists within P steps).  Only worth it for narrow rows (N + 1 <= 2 P);
-// wider rows keep N + 1.
-inline int cs_row_stride(int N, int G, int word_bytes, int mult = 1) {
-    const int P = 128 / word_bytes;
+// cs row stride (entries) of the (cos, sin) pair rows.  One LDS phase serves 128 bytes = P lanes (P = 8 for 16-byte
+// pairs, 16 for 8-byte pairs); with G < P lanes per sample a phase spans P / G consecutive sample rows, and the
+// lanes of a row read G different entries, so the rows must start G entries apart modulo P: stride = G (mod P).
+// Only worth it for narrow rows (N + 1 <= 2 P); wider rows keep N + 1.
+inline int cs_row_stride(int N, int G, int pair_bytes) {
+    const int P = 128 / pair_bytes;
     int np = N + 1;
     if (G < P && np <= 2 * P)
-        while ((mult * np) % P != G % P) ++np;
+        while (np % P != G % P) ++np;
     return np;
 }
 

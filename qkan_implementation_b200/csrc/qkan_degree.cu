@@ -53,41 +53,58 @@ struct GramParams {
     int S;                 // sample slices
 };
 
-// fill one side's chunk: rows = samples s0 .. s0 + KC, columns c0 .. c0 + TILE of the augmented matrix
-template <int MAXI>
-__device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI], int items,
+// fill one side's chunk: rows = samples s0 .. s0 + KC, columns c0 .. c0 + TILE of the augmented matrix.
+// D1T > 0: D + 1 is the compile-time constant D1T (unrolled recurrence, immediate store offsets).
+template <int MAXI, int D1T>
+__device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI],
                                            int f_lo, int nf) {
     // item = (feature slot j, sample kk) with kk = t % 32 fastest: thread t handles slots t / 32, t / 32 + 4, ...;
     // the values were prefetched into xv[]
-    const int D1 = p.D + 1;
+    const int D1 = D1T > 0 ? D1T : p.D + 1;
     const int kk = threadIdx.x & (KC - 1);
-    const bool live = s0 + kk < p.n;
+    const double lv = s0 + kk < p.n ? 1.0 : 0.0;         // rows beyond the slice are zero rows (last chunk only)
 #pragma unroll
     for (int it = 0; it < MAXI; ++it) {
         const int j = (threadIdx.x >> 5) + it * (GRAM_THREADS / KC);
         if (j > nf) break;
         if (j == nf) {                                   // the y column (if this tile holds it) and the padding beyond P
             const int cy = p.P - c0;
-            if (cy >= 0 && cy < TILE) dst[cy * LDK + kk] = live ? xv[it] : 0.0;
+            if (cy >= 0 && cy < TILE) dst[cy * LDK + kk] = lv * xv[it];
             for (int c = (cy >= 0 ? cy + 1 : 0); c < TILE; ++c)
                 if (c0 + c > p.P) dst[c * LDK + kk] = 0.0;
             continue;
         }
         const int f = f_lo + j;
         const double xc = clip_unit(xv[it]);
-        double t0 = 1.0, t1 = xc;
         const int cbase = f * D1 - c0;                   // tile column of degree 0 of this feature
-        for (int k = 0; k < D1; ++k) {
-            const double tk = k == 0 ? 1.0 : t1;
-            const int c = cbase + k;
-            if (c >= 0 && c < TILE && f < p.F) dst[c * LDK + kk] = live ? tk : 0.0;
-            if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+        double* q = dst + cbase * LDK + kk;
+        double t0 = lv, t1 = lv * xc;                    // T_0, T_1 (times the row's 0 / 1)
+        if (cbase >= 0 && cbase + D1 <= TILE && f < p.F) {       // the feature's columns lie inside the tile: no checks
+            q[0] = t0;
+#pragma unroll
+            for (int k = 1; k < (D1T > 0 ? D1T : 1); ++k) {
+                q[k * LDK] = t1;
+                const double t2 = 2.0 * xc * t1 - t0;
+                t0 = t1; t1 = t2;
+            }
+            if (D1T == 0)
+                for (int k = 1; k < D1; ++k) {
+                    q[k * LDK] = t1;
+                    const double t2 = 2.0 * xc * t1 - t0;
+                    t0 = t1; t1 = t2;
+                }
+        } else if (f < p.F) {                            // a feature cut by the tile edge
+            for (int k = 0; k < D1; ++k) {
+                const int c = cbase + k;
+                if (c >= 0 && c < TILE) q[k * LDK] = k == 0 ? t0 : t1;
+                if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+            }
         }
     }
 }
 
 // MAXI = most feature slots a thread fills per chunk and side: (64 / (D+1) + 2 features + the y slot) / 4
-template <int MAXI>
+template <int MAXI, int D1T>
 __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
     __shared__ __align__(16) double As[TILE * LDK];
     __shared__ __align__(16) double Bs[TILE * LDK];
@@ -107,7 +124,6 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
         return n;
     };
     const int nfa = nfeat(ca, fa_lo), nfb = nfeat(cb, fb_lo);
-    const int items_a = 0, items_b = 0;                  // (slot counts follow from nfa / nfb)
     double xa[MAXI], xb[MAXI];
 
     const long long per = (p.n + p.S - 1) / p.S;
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
     long long s_end = s_begin + per;
     if (s_end > p.n) s_end = p.n;
 
-    auto prefetch = [&](long long s0, double (&xv)[MAXI], int, int f_lo, int nf) {
+    auto prefetch = [&](long long s0, double (&xv)[MAXI], int f_lo, int nf) {
         const int kk = threadIdx.x & (KC - 1);
 #pragma unroll
         for (int it = 0; it < MAXI; ++it) {
@@ -143,17 +159,17 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
     GramParams q = p;
     q.n = s_end;
     if (s_begin < s_end) {
-        prefetch(s_begin, xa, items_a, fa_lo, nfa);
-        if (!diag) prefetch(s_begin, xb, items_b, fb_lo, nfb);
+        prefetch(s_begin, xa, fa_lo, nfa);
+        if (!diag) prefetch(s_begin, xb, fb_lo, nfb);
     }
     for (long long s0 = s_begin; s0 < s_end; s0 += KC) {
         __syncthreads();                                 // the previous chunk's fragments are consumed
-        fill_chunk<MAXI>(q, As, s0, ca, xa, items_a, fa_lo, nfa);
-        if (!diag) fill_chunk<MAXI>(q, Bs, s0, cb, xb, items_b, fb_lo, nfb);
+        fill_chunk<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
+        if (!diag) fill_chunk<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
         __syncthreads();
         if (s0 + KC < s_end) {                           // next chunk's x / y: in flight during the MMAs
-            prefetch(s0 + KC, xa, items_a, fa_lo, nfa);
-            if (!diag) prefetch(s0 + KC, xb, items_b, fb_lo, nfb);
+            prefetch(s0 + KC, xa, fa_lo, nfa);
+            if (!diag) prefetch(s0 + KC, xb, fb_lo, nfb);
         }
         const double* Bsrc = diag ? As : Bs;
 #pragma unroll
@@ -342,9 +358,15 @@ extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F
     p.T = (p.P + 1 + TILE - 1) / TILE;
     p.S = S;
     const int n_tiles = p.T * (p.T + 1) / 2;
-    if (D >= 3) qkan_cheb_gram_kernel<5><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);        // <= 18 slots per side
-    else if (D >= 1) qkan_cheb_gram_kernel<9><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);   // <= 34
-    else qkan_cheb_gram_kernel<17><<<dim3(n_tiles, S), GRAM_THREADS, 0, stream>>>(p);              // 65
+    const dim3 grid(n_tiles, S);
+    switch (D) {                                             // slots per side <= 64 / (D+1) + 2 features + y
+        case 0: qkan_cheb_gram_kernel<17, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 1: qkan_cheb_gram_kernel<9, 2><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 2: qkan_cheb_gram_kernel<9, 3><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 3: qkan_cheb_gram_kernel<5, 4><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 4: qkan_cheb_gram_kernel<5, 5><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        default: qkan_cheb_gram_kernel<5, 0><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");
     qkan_cheb_gram_reduce_kernel<<<n_tiles, 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);
@@ -387,6 +409,60 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qkan_cheb_residual_kernel)");
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_residual_kernel launch");
+    return QKAN_OK;
+}
+
+// ---- FP64 tensor-core peak: independent DMMA accumulator chains on every SM (the Gram kernel's roofline denominator)
+namespace {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* sink, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = (double)(threadIdx.x + i) * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma_m8n8k4(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    if (s == 123456.789) sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int qkan_measure_dmma_peak(int device, double* tflops) {
+    if (!tflops) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int grid = sms * 8, nt = 256, iters = 4096;
+    double* sink = nullptr;
+    e = cudaMalloc(&sink, (size_t)grid * nt * sizeof(double));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<grid, nt>>>(sink, iters, 1e-3, 1e-3);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        // one m8n8k4 per warp = 8 * 8 * 4 multiply-adds = 512 flops
+        const double fl = 512.0 * 8 * 2 * (double)iters * grid * (nt / 32);
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "dmma_peak_kernel");
+    *tflops = best;
     return QKAN_OK;
 }
 

@@ -221,6 +221,12 @@ extern "C" int qkan_emu_block_forward(int amp, int mode, int min_g, int tan, con
     BCASE(2, Real, double, 0, 4) BCASE(2, Real, double, 0, 2) BCASE(2, Real, double, 0, 1)
     return -2;
 }
+// host helpers of the block engine, exported for property tests
+extern "C" int qkan_emu_tan_row_words(int N, int G, int word_bytes) { return tan_row_words(N, G, word_bytes); }
+extern "C" int qkan_emu_cs_row_stride(int N, int G, int pair_bytes) { return cs_row_stride(N, G, pair_bytes); }
+extern "C" void qkan_emu_block_window(int N, int K, int g_k_log2, int bi, int* lo, int* len) { block_window(N, K, g_k_log2, bi, lo, len); }
+extern "C" int qkan_emu_block_window_max(int N, int K, int g_k_log2, int brows) { return block_window_max(N, K, g_k_log2, brows); }
+
 extern "C" void qkan_emu_block_layout(int N, int K, int D, int min_g, int* out6, double* eff) {
     const BlockLayout l = plan_block_layout(N, K, D, min_g);
     out6[0] = l.U; out6[1] = l.g_r_log2; out6[2] = l.g_k_log2; out6[3] = l.passes; out6[4] = l.brows;

@@ -76,3 +76,40 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
         assert np.abs(out - ref).max() <= tol
         assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
         assert np.abs(amps[..., 1]).max() == 0.0
+
+
+def test_row_strides_are_bank_conflict_free(emu):
+    """tan_row_words / cs_row_stride: the lanes of one shared-memory phase (128 bytes) that read the same member of G
+    consecutive entries in P / G consecutive sample rows must land on different banks (G = 4, 8, 16 in FP64)."""
+    for N, G in ((4, 4), (8, 8), (16, 16), (5, 4), (3, 2), (12, 8)):
+        for wb in (8, 4):
+            P = 128 // wb
+            rsw = emu.qkan_emu_tan_row_words(N, G, wb)
+            assert rsw >= 3 * (N + 1)
+            banks = [((lane // G) * rsw + 3 * (lane % G)) % P for lane in range(P)] if G < P else list(range(P))
+            worst = max(banks.count(b) for b in set(banks))
+            assert worst == 1 or G not in (4, 8, 16), (N, G, wb, rsw, worst)
+        np16 = emu.qkan_emu_cs_row_stride(N, G, 16)
+        assert np16 >= N + 1
+        if G < 8:
+            banks = [((lane // G) * np16 + lane % G) % 8 for lane in range(8)]
+            assert len(set(banks)) == 8
+
+
+def test_input_windows_cover_every_block(emu):
+    """block_window: row step bi reads x[(a + N b) / K] for its rows b only inside [lo, lo + len), windows are
+    monotone, and block_window_max bounds them."""
+    import ctypes
+    for N, K, gk in ((784, 10, 0), (784, 10, 1), (100, 10, 0), (33, 3, 1), (600, 16, 2), (7, 5, 0), (5, 8, 1), (1000, 3, 0)):
+        Gk = 1 << gk
+        brows = (K + Gk - 1) // Gk
+        wmax = emu.qkan_emu_block_window_max(N, K, gk, brows)
+        prev_lo = -1
+        for bi in range(brows):
+            lo, ln = ctypes.c_int(), ctypes.c_int()
+            emu.qkan_emu_block_window(N, K, gk, bi, ctypes.byref(lo), ctypes.byref(ln))
+            assert 1 <= ln.value <= wmax and lo.value >= prev_lo
+            prev_lo = lo.value
+            rows = [b for b in range(bi * Gk, min(K, (bi + 1) * Gk))]
+            idx = [(a + N * b) // K for b in rows for a in range(N)]
+            assert min(idx) == lo.value and max(idx) == lo.value + ln.value - 1

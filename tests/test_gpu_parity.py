@@ -307,6 +307,33 @@ def test_c_abi_forward_peers_multi_store(Q):
 
 
 # ------------------------------------------------- full-size, size-independent properties
+@pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:128:4:4"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"}, {"QKAN_BLOCK_TUNE": "1:128:5:2"},
+                                 {"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"},
+                                 {"QKAN_BLOCK_STRIDED": "1"}, {"QKAN_BLOCK_STRIDED": "0"}, {"QKAN_BLOCK_SUB": "1"},
+                                 {"QKAN_BLOCK_SUB": "2"}, {"QKAN_BLOCK_NO_WINDOW": "1"}, {"QKAN_HOST_PATH": "staged"}])
+def test_tuning_variants_agree(Q, env, monkeypatch):
+    """Every kernel variant / schedule reachable through the tuning knobs gives the oracle's numbers on ragged batches
+    (the knobs are read at layer creation / launch)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for (N, K, D, B) in ((4, 4, 3, 1), (4, 4, 3, 1029), (8, 8, 2, 70_001), (8, 8, 4, 333), (16, 16, 8, 77), (100, 10, 5, 130)):
+        rng = np.random.default_rng(B + N)
+        x = rng.uniform(-1, 1, (B, N))
+        W = rng.uniform(-1, 1, (D + 1, N * K))
+        ref = o.forward_closed_form(x, W, N, K, D)
+        try:
+            layer = Q.QKANLayer(N, K, D)
+            y = layer.forward(torch.from_numpy(x).cuda(), torch.from_numpy(W).cuda())
+        except Q._binding.QkanError as e:      # a forced (U, CTA, SU) combination is not built for every degree / shape
+            assert "QKAN_BLOCK_TUNE" in env and e.code == -2, e
+            continue
+        assert_close(y.cpu().numpy(), ref)
+        xp = torch.from_numpy(x).pin_memory()
+        op = torch.empty((B, K), dtype=torch.float64).pin_memory()
+        layer.forward(xp.numpy(), W, out=op.numpy(), check_range=False)          # pinned: zero-copy (or staged by env)
+        assert_close(op.numpy(), ref)
+
+
 @pytest.mark.parametrize("N,K,D,B", [(4, 4, 3, 1_000_000),        # BASELINE configs[1]
                                      (16, 16, 8, 1_000_000),     # configs[2]
                                      (784, 10, 5, 100_000),      # configs[3]

@@ -95,17 +95,21 @@ class ChebyshevLeastSquares:
         return s.cpu().numpy(), t.cpu().numpy(), (xr.cpu().numpy() if want_xtr else None)
 
     @staticmethod
-    def _pinv_solve(A: np.ndarray, b: np.ndarray, n: int) -> np.ndarray:
-        """Minimum-norm least-squares solution from the normal equations (what np.linalg.lstsq returns for the
-        rank-deficient X_d: the T_0 columns of all features are identical).  Eigenvalues below the larger of lstsq's
-        own cut-off (rcond = eps max(n, P) on singular values) and the resolution of a Gram matrix are dropped."""
+    def _pinv_factor(A: np.ndarray, n: int):
+        """Eigen-factor of a leading Gram block for minimum-norm least-squares solves (what np.linalg.lstsq returns
+        for the rank-deficient X_d: the T_0 columns of all features are identical).  Eigenvalues below the larger of
+        lstsq's own cut-off (rcond = eps max(n, P) on singular values) and the resolution of a Gram matrix are dropped."""
         lam, V = np.linalg.eigh(A)
         eps = np.finfo(np.float64).eps
-        P = len(b)
+        P = A.shape[0]
         cut = lam[-1] * max((eps * max(n, P)) ** 2, 64.0 * P * eps)
         keep = lam > cut
-        Vk = V[:, keep]
-        return Vk @ ((Vk.T @ b) / lam[keep])
+        return V[:, keep], lam[keep]
+
+    @staticmethod
+    def _pinv_apply(factor, b: np.ndarray) -> np.ndarray:
+        Vk, lam = factor
+        return Vk @ ((Vk.T @ b) / lam)
 
     def solve(self, x, y, weights=None, refine: int = 1):
         """x [n, F], y [n], weights [n] or None -> (scores [D+1] = MSE, comp_r2 [D+1]) as evaluate_degree."""
@@ -126,14 +130,16 @@ class ChebyshevLeastSquares:
         ybar = G[0, P] / n_all                               # column 0 = T_0 of feature 0 = ones
         n_local, n = n, n_all
         coef = np.zeros((D1, P))
+        factors = []
         for d in range(D1):
             Pd = F * (d + 1)
-            coef[d, :Pd] = self._pinv_solve(G[:Pd, :Pd], G[:Pd, P], n)
+            factors.append(self._pinv_factor(G[:Pd, :Pd], n))
+            coef[d, :Pd] = self._pinv_apply(factors[d], G[:Pd, P])
         for _ in range(max(0, refine)):                      # iterative refinement on the explicit residuals
             _, _, xr = self.residual_sums(x, y, w, coef, ybar, True)
             for d in range(D1):
                 Pd = F * (d + 1)
-                coef[d, :Pd] += self._pinv_solve(G[:Pd, :Pd], xr[d, :Pd], n)
+                coef[d, :Pd] += self._pinv_apply(factors[d], xr[d, :Pd])
         s, t, _ = self.residual_sums(x, y, w, coef, ybar, False)
         scores, comp_r2 = np.zeros(D1), np.zeros(D1)
         eps = np.finfo(float).eps

@@ -110,7 +110,7 @@ typedef struct {
     int passes_survey, passes_exec;
     int scaled_rotations;       /* 1: CHEB passes run in the scaled form Ry = gamma * M(t), one FMA per real output,
                                    gamma^D and the quarter turns deferred to the last pass (block engine, compat
-                                   mode, 2 <= D <= 16); 0: plain (cos, sin) rotations                         */
+                                   mode, 1 <= D <= 16); 0: plain (cos, sin) rotations                         */
     int input_window;           /* > 0: window kernel (wide input rows) - rotation entries are built per row step
                                    from this many inputs instead of once per sample from all N                 */
     double flops_survey;        /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)                     */

@@ -275,7 +275,7 @@ QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Scaled-rotation form of the CHEB sequence (compat mode, compile-time degree DT >= 2).
+// Scaled-rotation form of the CHEB sequence (compat mode, compile-time degree DT >= 1).
 //
 // Ry(theta_x) = [[c, -s], [s, c]] is a scalar times a matrix with a unit diagonal:
 //     |c| >= s :  Ry = c * M(t),       t =  s / c,    M(t) = [[1, -t], [t, 1]]

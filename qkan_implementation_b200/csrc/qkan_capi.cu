@@ -144,7 +144,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // wide input rows (the main path found nothing, or had to fall back to the U = 4 (cos, sin) kernels because
         // the rotation entries of whole input rows left room for < 24 warps per SM): the window kernel builds the
         // entries per row step from the step's input window (N784 K10 D5: 4.0 -> 6.3 M samples/s).  Scaled-rotation
-        // form only (compat mode, 2 <= D <= 16).
+        // form only (compat mode, 1 <= D <= 16).
         if (use_tan_form(mode, tan_dt ? max_degree : 0, 1) && fU <= 1 && !getenv("QKAN_BLOCK_NO_WINDOW")) {
             const bool bound = !bbest || bbest->U == 4;
             // narrowest lane group whose window tile leaves room for four (else three) 256-thread CTAs per SM

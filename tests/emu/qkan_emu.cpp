@@ -117,7 +117,7 @@ template <class A, typename R, int U> struct TanRun<A, R, U, 0> {
     static void go(int, const A (&)[4], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], const R (&)[U], A&) {}
 };
 
-// tan != 0: the scaled-rotation form of the degree-specialised kernels (compat mode, 2 <= D <= 16);
+// tan != 0: the scaled-rotation form of the degree-specialised kernels (compat mode, 1 <= D <= 16);
 // tan == 2: the window kernel's tables and per-row-step input windows (U = 1 layouts only)
 template <class A, typename R, int U, int MODE>
 int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, int tan, double* out, double* amps) {

@@ -199,15 +199,13 @@ class DegreeOptimizer:
         self._build_layer()
 
     def _build_layer(self) -> None:
+        """Weights of :63-76: W[d][out_idx * N + in_idx] = 1 where the connection (out_idx, in_idx) has degree d."""
         N, K = self.network_shape[0], self.network_shape[1]
         self.qkan_layer = QKANLayer(N=N, K=K, max_degree=self.max_degree)
-        for d in range(self.max_degree + 1):                 # :63-76
-            w = np.zeros(N * K)
-            for out_idx, connections in enumerate(self.optimal_degrees):
-                for in_idx, degree in enumerate(connections):
-                    if degree == d:
-                        w[out_idx * N + in_idx] = 1.0
-            self.qkan_layer.mul_step.set_weights(d, w)
+        degrees = np.asarray(self.optimal_degrees, dtype=np.int64).reshape(K, N)
+        onehot = (degrees.reshape(1, K * N) == np.arange(self.max_degree + 1)[:, None]).astype(np.float64)
+        for d in range(self.max_degree + 1):
+            self.qkan_layer.mul_step.set_weights(d, onehot[d])
 
     def predict(self, x_data) -> np.ndarray:
         """:78-95, for the whole batch in one launch (the reference's 2-D call raises in MulStep.py:62-66);
@@ -239,18 +237,13 @@ class DegreeOptimizer:
         return scores, comp_r2
 
     def is_degree_definitive(self, scores: np.ndarray) -> Tuple[bool, int]:
-        """:159-181."""
-        best_degree = int(np.argmin(scores))
-        best_score = float(scores[best_degree])
-        is_definitive = True
-        for d in range(len(scores)):
-            if d != best_degree:
-                score = float(scores[d])
-                relative_improvement = (score - best_score) / (score + 1e-10)
-                if relative_improvement < self.significance_threshold:
-                    is_definitive = False
-                    break
-        return is_definitive, best_degree
+        """:159-181: the best (lowest-score) degree is definitive when every other degree is worse by at least
+        `significance_threshold`, relative to its own score."""
+        sc = np.asarray(scores, dtype=np.float64)
+        best = int(np.argmin(sc))
+        others = np.delete(sc, best)
+        gain = (others - sc[best]) / (others + 1e-10)
+        return bool(np.all(gain >= self.significance_threshold)), best
 
     def optimize_layer(self, layer_idx: int, x_data, y_data, weights, num_reads: int = 1000) -> List[List[int]]:
         """:183-253.  The reference compiles a QUBO and samples it with neal; its objective is a sum over functions of
@@ -275,70 +268,53 @@ class DegreeOptimizer:
                 for layer in range(self.num_layers)]
 
     def _compute_metrics(self, y_true, y_pred, weights=None) -> Dict[str, float]:
-        """:277-312 for explicit predictions (host arithmetic on the caller's arrays, as in the reference)."""
-        y_true = np.asarray(y_true).reshape(-1, 1)
-        y_pred = np.asarray(y_pred).reshape(-1, 1)
-        squared_errors = (y_true - y_pred) ** 2
-        if weights is not None:
-            weights = np.asarray(weights).reshape(-1, 1)
-            mse = np.average(squared_errors, weights=weights)
-            ss_tot = np.sum(weights * squared_errors)
-            ss_res = np.sum(weights * y_true ** 2)
+        """:277-312 for explicit predictions (host arithmetic on the caller's arrays, as in the reference).  The
+        reference's naming is kept: weighted branch 'ss_tot' = sum w err^2, 'ss_res' = sum w y^2; r2 = 1 - ss_tot / ss_res."""
+        yt = np.asarray(y_true).reshape(-1, 1)
+        err2 = (yt - np.asarray(y_pred).reshape(-1, 1)) ** 2
+        if weights is None:
+            mse, ss_tot, ss_res = np.mean(err2), np.sum((yt - np.mean(yt)) ** 2), np.sum(err2)
         else:
-            mse = np.mean(squared_errors)
-            ss_tot = np.sum((y_true - np.mean(y_true)) ** 2)
-            ss_res = np.sum(squared_errors)
+            w = np.asarray(weights).reshape(-1, 1)
+            mse, ss_tot, ss_res = np.average(err2, weights=w), np.sum(w * err2), np.sum(w * yt ** 2)
         if ss_tot < np.finfo(float).eps:
             print(f"Warning: Total sum of squares ({ss_tot}) near zero - data might be over-normalized")
-            r2 = 0.0
-        else:
-            r2 = 1 - ss_tot / ss_res
-        return {'mse': float(mse), 'r2': float(r2)}
+            return {'mse': float(mse), 'r2': 0.0}
+        return {'mse': float(mse), 'r2': float(1 - ss_tot / ss_res)}
 
     # ------------------------------------------------------------------ state (:313-375)
+    _DEFAULT_QUERY = {'n_rows': 100000,
+                      'columns': ['date_id', 'responder_6', 'weight'] + [f'feature_{i:02d}' for i in range(79)],
+                      'sort_by': 'date_id'}
+    _HYPER = ('network_shape', 'max_degree', 'complexity_weight', 'significance_threshold')
+
     def save_state(self, filename: str, query_params: Dict = None) -> None:
-        if query_params is None:
-            query_params = {'n_rows': 100000,
-                            'columns': ['date_id', 'responder_6', 'weight'] + [f'feature_{i:02d}' for i in range(79)],
-                            'sort_by': 'date_id'}
-        qkan_params = None
+        """Same .npy dictionary as the reference (keys and nesting), so states are interchangeable."""
+        state = {k: getattr(self, k) for k in self._HYPER}
+        state.update(transform_cache=self.transform_cache, degree_scores=self.degree_scores,
+                     query_params=dict(self._DEFAULT_QUERY) if query_params is None else query_params, qkan_params=None)
         if self.qkan_layer is not None:
-            qkan_params = {'weights': [self.qkan_layer.mul_step._weights[d].copy() for d in range(self.max_degree + 1)],
-                           'feature_means': self.feature_means.copy(), 'feature_stds': self.feature_stds.copy(),
-                           'optimal_degrees': list(self.optimal_degrees)}
-        state = {'network_shape': self.network_shape, 'max_degree': self.max_degree,
-                 'complexity_weight': self.complexity_weight, 'significance_threshold': self.significance_threshold,
-                 'transform_cache': self.transform_cache, 'degree_scores': self.degree_scores,
-                 'query_params': query_params, 'qkan_params': qkan_params}
+            state['qkan_params'] = {'weights': [w.copy() for w in self.qkan_layer.mul_step._weights],
+                                    'feature_means': self.feature_means.copy(), 'feature_stds': self.feature_stds.copy(),
+                                    'optimal_degrees': list(self.optimal_degrees)}
         np.save(filename, state)
 
     def load_state(self, filename: str, current_query_params: dict) -> None:
         state = np.load(filename, allow_pickle=True).item()
-        self.network_shape = state['network_shape']
+        for k in self._HYPER:
+            setattr(self, k, state[k])
         self.num_layers = len(self.network_shape) - 1
-        self.max_degree = state['max_degree']
-        self.complexity_weight = state['complexity_weight']
-        self.significance_threshold = state['significance_threshold']
-        if state['qkan_params'] is not None:
-            qp = state['qkan_params']
-            self.feature_means = qp['feature_means']
-            self.feature_stds = qp['feature_stds']
-            self.optimal_degrees = qp['optimal_degrees']
-            N, K = self.network_shape[0], self.network_shape[1]
-            self.qkan_layer = QKANLayer(N=N, K=K, max_degree=self.max_degree)
-            for d, weights in enumerate(qp['weights']):
-                self.qkan_layer.mul_step.set_weights(d, weights)
-        if self._validate_query(state['query_params'], current_query_params):
-            print("Loading cached computations")
-            self.transform_cache = state['transform_cache']
-            self.degree_scores = state['degree_scores']
-        else:
-            print("Query changed, clearing caches")
-            self.data_same = False
-            self.transform_cache = {}
-            self.degree_scores = {}
+        qp = state['qkan_params']
+        if qp is not None:
+            self.feature_means, self.feature_stds, self.optimal_degrees = qp['feature_means'], qp['feature_stds'], qp['optimal_degrees']
+            self.qkan_layer = QKANLayer(N=self.network_shape[0], K=self.network_shape[1], max_degree=self.max_degree)
+            for d, w in enumerate(qp['weights']):
+                self.qkan_layer.mul_step.set_weights(d, w)
+        same = self._validate_query(state['query_params'], current_query_params)
+        print("Loading cached computations" if same else "Query changed, clearing caches")
+        self.data_same = self.data_same and same
+        self.transform_cache = state['transform_cache'] if same else {}
+        self.degree_scores = state['degree_scores'] if same else {}
 
     def _validate_query(self, saved_params: dict, current_query_params: dict) -> bool:
-        return (saved_params['n_rows'] == current_query_params['n_rows'] and
-                saved_params['columns'] == current_query_params['columns'] and
-                saved_params['sort_by'] == current_query_params['sort_by'])
+        return all(saved_params[k] == current_query_params[k] for k in ('n_rows', 'columns', 'sort_by'))

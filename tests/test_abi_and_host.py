@@ -44,6 +44,22 @@ def test_abi_argument_errors_without_gpu():
     assert lib.qkan_layer_forward(None, None, 1, None, None, None) == b.ERR_BAD_SHAPE
 
 
+def test_degree_abi_argument_errors_without_gpu():
+    from qkan_implementation_b200 import _binding as b
+    lib = b.lib()
+    need, slices = ctypes.c_int64(), ctypes.c_int()
+    assert lib.qkan_cheb_gram_workspace(774_456, 79, 3, ctypes.byref(need), ctypes.byref(slices)) == 0
+    assert need.value == slices.value * 15 * 64 * 64 * 8 and slices.value >= 1      # 5 x 5 tiles, upper triangle
+    assert lib.qkan_cheb_gram_workspace(100, 79, 17, ctypes.byref(need), None) == b.ERR_BAD_SHAPE   # D <= 16
+    assert lib.qkan_cheb_gram(None, None, 10, 3, 2, None, None, 0, None) == b.ERR_BAD_SHAPE
+    assert lib.qkan_cheb_residuals(None, None, None, 10, 3, 2, None, 0.0, None, None, None, None) == b.ERR_BAD_SHAPE
+    assert lib.qkan_cheb_features(None, 10, 3, 2, None, None) == b.ERR_BAD_SHAPE
+    if not torch.cuda.is_available():
+        from qkan_implementation_b200 import DegreeOptimizer
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            DegreeOptimizer([3, 1], 2).evaluate_degree(np.zeros((5, 3)), np.zeros(5))
+
+
 def test_no_cpu_fallback_when_no_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

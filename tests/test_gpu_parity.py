@@ -307,6 +307,28 @@ def test_c_abi_forward_peers_multi_store(Q):
 
 
 # ------------------------------------------------- full-size, size-independent properties
+@pytest.mark.parametrize("N,K,D", [(4, 4, 1), (4, 4, 3), (8, 8, 2), (8, 8, 16), (16, 16, 8), (784, 10, 5), (5, 3, 7)])
+def test_special_input_values(Q, N, K, D):
+    """The scaled-rotation pre-pass (one rsqrt, quarter-turn switch at |x| = 1/sqrt 2) at its edge cases: +-1, +-0,
+    denormals, values next to the switch, values next to 1, clipped and infinite inputs."""
+    r = np.sqrt(0.5)
+    specials = np.array([1.0, -1.0, 0.0, -0.0, 1e-300, -1e-300, 5e-324, r, -r, np.nextafter(r, 1), np.nextafter(r, 0),
+                         np.nextafter(1.0, 0), -np.nextafter(1.0, 0), 1.0 + 1e-9, -3.0, np.inf, -np.inf, 0.5, 1e-8, -1e-160])
+    rng = np.random.default_rng(N + D)
+    B = 64
+    x = rng.choice(specials, size=(B, N))
+    x[0, :] = specials[np.arange(N) % len(specials)]
+    x[1, :] = specials[(np.arange(N) + 7) % len(specials)]
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    W.flat[:6] = [1.0, -1.0, 0.0, 1e-300, r, -r][:W.size]
+    ref = o.forward_closed_form(x, W, N, K, D)
+    assert np.isfinite(ref).all()
+    for dtype in ("complex128", "complex64", "real64"):
+        y = Q.QKANLayer(N, K, D, dtype=dtype).forward(x, W, check_range=False)
+        assert np.isfinite(y).all()
+        assert_close(y, ref, dtype)
+
+
 @pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:128:4:4"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"}, {"QKAN_BLOCK_TUNE": "1:128:5:2"},
                                  {"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"},
                                  {"QKAN_BLOCK_STRIDED": "1"}, {"QKAN_BLOCK_STRIDED": "0"}, {"QKAN_BLOCK_SUB": "1"},

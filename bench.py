@@ -380,13 +380,13 @@ def run_ours(a):
         pipe_util = info["fp_inst_exec"] * B / (k_ms * 1e-3) / (peak * 1e12 / 2.0)
         io = (8 * a.N + 8 * a.K) * B
         # DRAM bytes per launch of the dominant kernel from the ncu --set full capture of this workload
-        # (profiles/r01c_ncu_c2.txt: dram__bytes_read 32.03 MB + dram__bytes_write 0.28 MB; the 32 MB of outputs
+        # (profiles/r01d_ncu_c2.txt: dram__bytes_read 32.03 MB + dram__bytes_write 0.20 MB; the 32 MB of outputs
         # stay in the 126 MB L2).  Only known for the default workload.
         traffic = None
         if (a.N, a.K, a.D, a.batch, a.dtype, a.prep, a.mode) == (4, 4, 3, 1_000_000, "complex128", "analytic", "compat"):
-            traffic = 32.03e6 + 0.28e6
+            traffic = 32.03e6 + 0.20e6
         roofline = {"bound": "fp64" if fp64 else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r01c_ncu_c2.txt (ncu --set full, per launch)" if traffic else None,
+                    "traffic": traffic, "traffic_source": "profiles/r01d_ncu_c2.txt (ncu --set full, per launch)" if traffic else None,
                     "kernel_ms": k_ms,
                     "fp_pipe_utilisation": pipe_util,
                     "flops_per_sample_executed": info["flops_exec"], "fp_instructions_per_sample": info["fp_inst_exec"],

@@ -33,6 +33,52 @@ def _as_device(a, device) -> torch.Tensor:
     return a.to(device=device, dtype=torch.float64).contiguous()
 
 
+class _NestedSolver:
+    """Minimum-norm least-squares solves X_d c = rhs for every degree d from the one Gram matrix of X_D.
+
+    The T_0 columns of all F features are the same all-ones column, so X_d always has rank <= 1 + F d and np.linalg.lstsq
+    returns the minimum-norm solution, which gives each of the F copies 1 / F of the constant's coefficient.  Fast path:
+    drop the copies (one ones column + the degree >= 1 columns) and take ONE Cholesky factor of that reduced Gram matrix -
+    its leading blocks are the factors of every lower degree.  If it is not comfortably positive definite (constant or
+    duplicated features, everything clipped, ...) fall back to an eigen-decomposition of each leading block with lstsq's
+    rank cut-off."""
+
+    def __init__(self, G: np.ndarray, n: int, F: int, D: int):
+        self.G, self.n, self.F, self.D = G, n, F, D
+        P = F * (D + 1)
+        self.red = np.r_[0, F:P]                             # reduced column set
+        self.L = None
+        self.eig = {}
+        try:
+            L = np.linalg.cholesky(G[np.ix_(self.red, self.red)])
+            dg = np.diag(L)
+            if dg.min() > 1e-6 * dg.max():
+                self.L = L
+        except np.linalg.LinAlgError:
+            pass
+
+    def solve(self, d: int, rhs: np.ndarray) -> np.ndarray:
+        F = self.F
+        Pd = F * (d + 1)
+        if self.L is not None:
+            m = 1 + F * d
+            Ld = self.L[:m, :m]
+            b = np.r_[rhs[0], rhs[F:Pd]]
+            z = _solve_triangular(Ld.T, _solve_triangular(Ld, b, lower=True), lower=False)
+            return np.r_[np.full(F, z[0] / F), z[1:]]
+        if d not in self.eig:
+            self.eig[d] = ChebyshevLeastSquares._pinv_factor(self.G[:Pd, :Pd], self.n)
+        return ChebyshevLeastSquares._pinv_apply(self.eig[d], rhs)
+
+
+def _solve_triangular(T, b, lower):
+    try:
+        from scipy.linalg import solve_triangular
+        return solve_triangular(T, b, lower=lower, check_finite=False)
+    except ImportError:                                      # pragma: no cover
+        return np.linalg.solve(T, b)
+
+
 class ChebyshevLeastSquares:
     """The GPU side of evaluate_degree: Gram matrix of [T_0(x) | ... | T_D(x) | y] (qkan_cheb_gram), the small
     minimum-norm solves on the host, explicit residual sums (qkan_cheb_residuals) with one step of iterative
@@ -130,16 +176,13 @@ class ChebyshevLeastSquares:
         ybar = G[0, P] / n_all                               # column 0 = T_0 of feature 0 = ones
         n_local, n = n, n_all
         coef = np.zeros((D1, P))
-        factors = []
+        solver = _NestedSolver(G, n, F, self.D)
         for d in range(D1):
-            Pd = F * (d + 1)
-            factors.append(self._pinv_factor(G[:Pd, :Pd], n))
-            coef[d, :Pd] = self._pinv_apply(factors[d], G[:Pd, P])
+            coef[d, :F * (d + 1)] = solver.solve(d, G[:F * (d + 1), P])
         for _ in range(max(0, refine)):                      # iterative refinement on the explicit residuals
             _, _, xr = self.residual_sums(x, y, w, coef, ybar, True)
             for d in range(D1):
-                Pd = F * (d + 1)
-                coef[d, :Pd] += self._pinv_apply(factors[d], xr[d, :Pd])
+                coef[d, :F * (d + 1)] += solver.solve(d, xr[d, :F * (d + 1)])
         s, t, _ = self.residual_sums(x, y, w, coef, ybar, False)
         scores, comp_r2 = np.zeros(D1), np.zeros(D1)
         eps = np.finfo(float).eps

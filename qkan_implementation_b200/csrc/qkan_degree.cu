@@ -222,7 +222,9 @@ __global__ void qkan_cheb_gram_reduce_kernel(const double* partial, int n_tiles,
 //   xtr[cta][d][P]  = X_D^T r_d   (optional)
 constexpr int RES_THREADS = 256;
 
-template <int D1>
+// JF > 0: F <= 32 JF and the X^T r accumulators of a lane (its JF features x D1 degrees x D1 fits) live in registers for
+// the whole launch, flushed once per warp at the end; JF = 0: any F, accumulation by shared-memory atomics per sample.
+template <int D1, int JF>
 __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const double* x, const double* y, const double* w, long long n, int F,
                                                                         const double* coef, double ybar, double* sums,
                                                                         double* tail, double* xtr) {
@@ -238,20 +240,47 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
 #pragma unroll
     for (int d = 0; d < D1; ++d) a_sse[d] = a_wsse[d] = 0.0;
     double a_tot = 0.0, a_wyy = 0.0, a_w = 0.0, a_y = 0.0;
+    constexpr int JR = JF > 0 ? JF : 1;
+    double a_x[JR][D1][D1];                              // [feature slot][degree k][fit d]
+#pragma unroll
+    for (int jj = 0; jj < JR; ++jj)
+#pragma unroll
+        for (int k = 0; k < D1; ++k)
+#pragma unroll
+            for (int d = 0; d < D1; ++d) a_x[jj][k][d] = 0.0;
     const long long gw = (long long)blockIdx.x * nwarp + warp, nw = (long long)gridDim.x * nwarp;
     for (long long s = gw; s < n; s += nw) {
         double pred[D1];
 #pragma unroll
         for (int d = 0; d < D1; ++d) pred[d] = 0.0;
-        for (int f = lane; f < F; f += 32) {
-            const double xc = clip_unit(x[s * F + f]);
-            double t0 = 1.0, t1 = xc;
+        double tv[JR][D1];                               // T_k of the lane's features (register path)
+        if constexpr (JF > 0) {
 #pragma unroll
-            for (int k = 0; k < D1; ++k) {
-                const double tk = k == 0 ? 1.0 : t1;
+            for (int jj = 0; jj < JF; ++jj) {
+                const int f = lane + 32 * jj;
+                const bool in = f < F;
+                const double xc = in ? clip_unit(x[s * F + f]) : 0.0;
+                double t0 = in ? 1.0 : 0.0, t1 = in ? xc : 0.0;
 #pragma unroll
-                for (int d = k; d < D1; ++d) pred[d] = fma(tk, coef[(size_t)d * P + k * F + f], pred[d]);
-                if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                for (int k = 0; k < D1; ++k) {
+                    const double tk = k == 0 ? t0 : t1;
+                    tv[jj][k] = tk;
+#pragma unroll
+                    for (int d = k; d < D1; ++d) pred[d] = fma(tk, in ? coef[(size_t)d * P + k * F + f] : 0.0, pred[d]);
+                    if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                }
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) {
+                const double xc = clip_unit(x[s * F + f]);
+                double t0 = 1.0, t1 = xc;
+#pragma unroll
+                for (int k = 0; k < D1; ++k) {
+                    const double tk = k == 0 ? 1.0 : t1;
+#pragma unroll
+                    for (int d = k; d < D1; ++d) pred[d] = fma(tk, coef[(size_t)d * P + k * F + f], pred[d]);
+                    if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                }
             }
         }
 #pragma unroll
@@ -270,15 +299,38 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
             a_y += yv;
         }
         if (xtr) {
-            for (int f = lane; f < F; f += 32) {
-                const double xc = clip_unit(x[s * F + f]);
-                double t0 = 1.0, t1 = xc;
+            if constexpr (JF > 0) {
 #pragma unroll
-                for (int k = 0; k < D1; ++k) {
-                    const double tk = k == 0 ? 1.0 : t1;
+                for (int jj = 0; jj < JF; ++jj)
 #pragma unroll
-                    for (int d = 0; d < D1; ++d) atomicAdd(&s_xtr[(size_t)d * P + k * F + f], tk * r[d]);
-                    if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                    for (int k = 0; k < D1; ++k)
+#pragma unroll
+                        for (int d = 0; d < D1; ++d) a_x[jj][k][d] = fma(tv[jj][k], r[d], a_x[jj][k][d]);
+            } else {
+                for (int f = lane; f < F; f += 32) {
+                    const double xc = clip_unit(x[s * F + f]);
+                    double t0 = 1.0, t1 = xc;
+#pragma unroll
+                    for (int k = 0; k < D1; ++k) {
+                        const double tk = k == 0 ? 1.0 : t1;
+#pragma unroll
+                        for (int d = 0; d < D1; ++d) atomicAdd(&s_xtr[(size_t)d * P + k * F + f], tk * r[d]);
+                        if (k >= 1) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (JF > 0) {
+        if (xtr) {                                       // one flush per warp
+#pragma unroll
+            for (int jj = 0; jj < JF; ++jj) {
+                const int f = lane + 32 * jj;
+                if (f < F) {
+#pragma unroll
+                    for (int k = 0; k < D1; ++k)
+#pragma unroll
+                        for (int d = 0; d < D1; ++d) atomicAdd(&s_xtr[(size_t)d * P + k * F + f], a_x[jj][k][d]);
                 }
             }
         }
@@ -292,10 +344,10 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
     }
     __syncthreads();
     if (threadIdx.x < Q) {
-        double s = 0.0;
-        for (int wq = 0; wq < nwarp; ++wq) s += s_red[wq * Q + threadIdx.x];
-        if (threadIdx.x < 2 * D1) sums[(size_t)blockIdx.x * 2 * D1 + threadIdx.x] = s;
-        else tail[(size_t)blockIdx.x * 4 + threadIdx.x - 2 * D1] = s;
+        double sacc = 0.0;
+        for (int wq = 0; wq < nwarp; ++wq) sacc += s_red[wq * Q + threadIdx.x];
+        if (threadIdx.x < 2 * D1) sums[(size_t)blockIdx.x * 2 * D1 + threadIdx.x] = sacc;
+        else tail[(size_t)blockIdx.x * 4 + threadIdx.x - 2 * D1] = sacc;
     }
     if (xtr)
         for (int i = threadIdx.x; i < D1 * P; i += RES_THREADS) xtr[(size_t)blockIdx.x * D1 * P + i] = s_xtr[i];
@@ -393,18 +445,29 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
     const size_t smem = ((xtr ? (size_t)D1 * P : 0) + (size_t)(RES_THREADS / 32) * (2 * D1 + 4)) * sizeof(double);
     if (smem > 200 * 1024) return fail(QKAN_ERR_UNSUPPORTED, "qkan_cheb_residuals: (D+1)^2 F too large for the refinement accumulators");
     cudaError_t e = cudaSuccess;
+#define QK_RES_LAUNCH(D1V, JFV)                                                                                                      \
+    {                                                                                                                                \
+        e = cudaFuncSetAttribute(qkan_cheb_residual_kernel<D1V, JFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        if (e == cudaSuccess)                                                                                                        \
+            qkan_cheb_residual_kernel<D1V, JFV><<<ctas, RES_THREADS, smem, (cudaStream_t)cuda_stream>>>(x, y, w, n, F, coef, ybar,   \
+                                                                                                     sums, tail, xtr);             \
+    }
+    // register accumulators for X^T r when a lane's share (ceil(F / 32) features x (D+1)^2) fits 64 doubles
 #define QK_RES_CASE(DD)                                                                                                              \
     case DD:                                                                                                                         \
-        e = cudaFuncSetAttribute(qkan_cheb_residual_kernel<DD + 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        if (e == cudaSuccess)                                                                                                        \
-            qkan_cheb_residual_kernel<DD + 1><<<ctas, RES_THREADS, smem, (cudaStream_t)cuda_stream>>>(x, y, w, n, F, coef, ybar,     \
-                                                                                                   sums, tail, xtr);               \
+        if (xtr && jf == 1 && 1 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, 1)                                                \
+        else if (xtr && jf == 2 && 2 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (2 * (DD + 1) * (DD + 1) <= 64 ? 2 : 0))     \
+        else if (xtr && jf == 3 && 3 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (3 * (DD + 1) * (DD + 1) <= 64 ? 3 : 0))     \
+        else if (xtr && jf == 4 && 4 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (4 * (DD + 1) * (DD + 1) <= 64 ? 4 : 0))     \
+        else QK_RES_LAUNCH(DD + 1, 0)                                                                                                \
         break;
+    const int jf = (F + 31) / 32;
     switch (D) {
         QK_RES_CASE(0) QK_RES_CASE(1) QK_RES_CASE(2) QK_RES_CASE(3) QK_RES_CASE(4) QK_RES_CASE(5) QK_RES_CASE(6) QK_RES_CASE(7)
         QK_RES_CASE(8) QK_RES_CASE(9) QK_RES_CASE(10) QK_RES_CASE(11) QK_RES_CASE(12) QK_RES_CASE(13) QK_RES_CASE(14)
         QK_RES_CASE(15) QK_RES_CASE(16)
     }
+#undef QK_RES_LAUNCH
 #undef QK_RES_CASE
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qkan_cheb_residual_kernel)");
     e = cudaGetLastError();

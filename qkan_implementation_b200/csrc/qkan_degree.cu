@@ -249,17 +249,36 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
 #pragma unroll
             for (int d = 0; d < D1; ++d) a_x[jj][k][d] = 0.0;
     const long long gw = (long long)blockIdx.x * nwarp + warp, nw = (long long)gridDim.x * nwarp;
+    // register path: the next sample's inputs are loaded while the current one is evaluated (the pass is latency bound)
+    double xn[JR], yn = 0.0, wn = 1.0;
+    auto load_sample = [&](long long s) {
+        if constexpr (JF > 0) {
+#pragma unroll
+            for (int jj = 0; jj < JF; ++jj) {
+                const int f = lane + 32 * jj;
+                xn[jj] = (s < n && f < F) ? x[s * F + f] : 0.0;
+            }
+            yn = s < n ? y[s] : 0.0;
+            wn = (s < n && w) ? w[s] : 1.0;
+        }
+    };
+    load_sample(gw);
     for (long long s = gw; s < n; s += nw) {
         double pred[D1];
 #pragma unroll
         for (int d = 0; d < D1; ++d) pred[d] = 0.0;
         double tv[JR][D1];                               // T_k of the lane's features (register path)
+        double xcur[JR];
+#pragma unroll
+        for (int jj = 0; jj < JR; ++jj) xcur[jj] = xn[jj];
+        const double ycur = yn, wcur = wn;
+        load_sample(s + nw);
         if constexpr (JF > 0) {
 #pragma unroll
             for (int jj = 0; jj < JF; ++jj) {
                 const int f = lane + 32 * jj;
                 const bool in = f < F;
-                const double xc = in ? clip_unit(x[s * F + f]) : 0.0;
+                const double xc = in ? clip_unit(xcur[jj]) : 0.0;
                 double t0 = in ? 1.0 : 0.0, t1 = in ? xc : 0.0;
 #pragma unroll
                 for (int k = 0; k < D1; ++k) {
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
 #pragma unroll
         for (int d = 0; d < D1; ++d)
             for (int m = 16; m >= 1; m >>= 1) pred[d] += __shfl_xor_sync(0xffffffffu, pred[d], m);
-        const double yv = y[s], wv = w ? w[s] : 1.0;
+        const double yv = JF > 0 ? ycur : y[s], wv = JF > 0 ? wcur : (w ? w[s] : 1.0);
         double r[D1];
 #pragma unroll
         for (int d = 0; d < D1; ++d) r[d] = yv - pred[d];
@@ -455,10 +474,10 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
     // register accumulators for X^T r when a lane's share (ceil(F / 32) features x (D+1)^2) fits 64 doubles
 #define QK_RES_CASE(DD)                                                                                                              \
     case DD:                                                                                                                         \
-        if (xtr && jf == 1 && 1 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, 1)                                                \
-        else if (xtr && jf == 2 && 2 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (2 * (DD + 1) * (DD + 1) <= 64 ? 2 : 0))     \
-        else if (xtr && jf == 3 && 3 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (3 * (DD + 1) * (DD + 1) <= 64 ? 3 : 0))     \
-        else if (xtr && jf == 4 && 4 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (4 * (DD + 1) * (DD + 1) <= 64 ? 4 : 0))     \
+        if (jf == 1 && 1 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, 1)                                                \
+        else if (jf == 2 && 2 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (2 * (DD + 1) * (DD + 1) <= 64 ? 2 : 0))     \
+        else if (jf == 3 && 3 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (3 * (DD + 1) * (DD + 1) <= 64 ? 3 : 0))     \
+        else if (jf == 4 && 4 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (4 * (DD + 1) * (DD + 1) <= 64 ? 4 : 0))     \
         else QK_RES_LAUNCH(DD + 1, 0)                                                                                                \
         break;
     const int jf = (F + 31) / 32;

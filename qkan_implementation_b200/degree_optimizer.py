@@ -84,23 +84,32 @@ class ChebyshevLeastSquares:
     minimum-norm solves on the host, explicit residual sums (qkan_cheb_residuals) with one step of iterative
     refinement."""
 
-    def __init__(self, max_degree: int, device: Optional[int] = None, group=None):
+    def __init__(self, max_degree: int, device: Optional[int] = None, group=None, kernels=None):
         """group: a torch.distributed process group (one process per GPU, NCCL).  Each rank then passes ITS rows to
         solve(); the Gram matrices and the residual sums of the ranks add up, so the only exchange is one all-reduce
-        of (P+1)^2 doubles and one of a few hundred - every rank returns the scores of the whole data set."""
+        of (P+1)^2 doubles and one of a few hundred - every rank returns the scores of the whole data set.
+        kernels: test seam (like ShardedQKANLayer's `compute`): an object with gram(x, y, D) and
+        residuals(x, y, w, D, coef, ybar, want_xtr) returning CPU tensors, so that the sharding / reduction / solve logic
+        can run under gloo without a GPU; the product path leaves it None and calls libqkan_b200.so."""
         self.group = group
         if not 0 <= max_degree <= 16:
             raise ValueError("the GPU degree evaluation covers 0 <= max_degree <= 16")
-        if not torch.cuda.is_available():
-            raise RuntimeError("qkan_implementation_b200 needs a CUDA device (no CPU fallback)")
+        self.kernels = kernels
         self.D = int(max_degree)
-        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if kernels is not None:
+            self.device = torch.device("cpu")
+        else:
+            if not torch.cuda.is_available():
+                raise RuntimeError("qkan_implementation_b200 needs a CUDA device (no CPU fallback)")
+            self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self.last = {}
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def gram(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if self.kernels is not None:
+            return self.kernels.gram(x, y, self.D)
         n, F = x.shape
         P = F * (self.D + 1)
         need, slices = ctypes.c_int64(), ctypes.c_int()
@@ -115,6 +124,9 @@ class ChebyshevLeastSquares:
     def residual_sums(self, x, y, w, coef: np.ndarray, ybar: float, want_xtr: bool):
         n, F = x.shape
         D1, P = self.D + 1, F * (self.D + 1)
+        if self.kernels is not None:
+            sums, tail, xtr = self.kernels.residuals(x, y, w, self.D, coef, ybar, want_xtr)
+            return self._reduce_residuals(sums, tail, xtr, want_xtr)
         ctas = ctypes.c_int()
         _b.check(_b.lib().qkan_cheb_residuals_ctas(ctypes.byref(ctas)))
         c = ctas.value
@@ -126,18 +138,21 @@ class ChebyshevLeastSquares:
             _b.check(_b.lib().qkan_cheb_residuals(x.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else None, n, F,
                                                   self.D, cd.data_ptr(), float(ybar), sums.data_ptr(), tail.data_ptr(),
                                                   xtr.data_ptr() if want_xtr else None, self._stream()))
-            # CTA partials are added in CTA order (deterministic), then the ranks' sums
-            s = sums.sum(dim=0)
-            t = tail.sum(dim=0)
-            xr = xtr.sum(dim=0) if want_xtr else None
-            if self.group is not None:
-                import torch.distributed as dist
-                packed = torch.cat([s.reshape(-1), t.reshape(-1)] + ([xr.reshape(-1)] if want_xtr else []))
-                dist.all_reduce(packed, group=self.group)
-                s = packed[:s.numel()].reshape(s.shape)
-                t = packed[s.numel():s.numel() + t.numel()].reshape(t.shape)
-                if want_xtr:
-                    xr = packed[s.numel() + t.numel():].reshape(xr.shape)
+            return self._reduce_residuals(sums, tail, xtr, want_xtr)
+
+    def _reduce_residuals(self, sums, tail, xtr, want_xtr):
+        """CTA partials are added in CTA order (deterministic), then the ranks' sums (one packed all-reduce)."""
+        s = sums.sum(dim=0)
+        t = tail.sum(dim=0)
+        xr = xtr.sum(dim=0) if want_xtr else None
+        if self.group is not None:
+            import torch.distributed as dist
+            packed = torch.cat([s.reshape(-1), t.reshape(-1)] + ([xr.reshape(-1)] if want_xtr else []))
+            dist.all_reduce(packed, group=self.group)
+            ns, nt = s.numel(), t.numel()
+            s, t = packed[:ns].reshape(s.shape), packed[ns:ns + nt].reshape(t.shape)
+            if want_xtr:
+                xr = packed[ns + nt:].reshape(xr.shape)
         return s.cpu().numpy(), t.cpu().numpy(), (xr.cpu().numpy() if want_xtr else None)
 
     @staticmethod

@@ -148,3 +148,73 @@ def test_sharded_forward_gloo_world2(B):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (B, 4) for _, _, shape in res)
+
+
+class _OracleKernels:
+    """CPU stand-in for the two degree-evaluation kernels (same outputs, one 'CTA'), so that the sharding / all-reduce /
+    solve logic of ChebyshevLeastSquares runs under gloo without a GPU."""
+
+    @staticmethod
+    def _design(x, D):
+        from oracle import degree_oracle as do
+        tr = do.chebyshev_transforms(x.numpy(), D)
+        return np.hstack([tr[d] for d in range(D + 1)])
+
+    def gram(self, x, y, D):
+        A = np.hstack([self._design(x, D), y.numpy()[:, None]])
+        return torch.from_numpy(A.T @ A)
+
+    def residuals(self, x, y, w, D, coef, ybar, want_xtr):
+        X, yv = self._design(x, D), y.numpy()
+        wv = w.numpy() if w is not None else np.ones_like(yv)
+        F = x.shape[1]
+        sums, xtr = np.zeros((1, D + 1, 2)), np.zeros((1, D + 1, X.shape[1]))
+        for d in range(D + 1):
+            r = yv - X[:, :F * (d + 1)] @ coef[d, :F * (d + 1)]
+            sums[0, d] = [np.sum(r * r), np.sum(wv * r * r)]
+            xtr[0, d] = X.T @ r
+        tail = np.array([[np.sum((yv - ybar) ** 2), np.sum(wv * yv * yv), np.sum(wv), np.sum(yv)]])
+        return torch.from_numpy(sums), torch.from_numpy(tail), (torch.from_numpy(xtr) if want_xtr else None)
+
+
+def _gloo_degree_worker(rank, world, port, weighted, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle import degree_oracle as do
+    from qkan_implementation_b200.degree_optimizer import ChebyshevLeastSquares
+    from qkan_implementation_b200.distributed import shard_bounds
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n, F, D = 1501, 6, 3
+    rng = np.random.default_rng(1)
+    x = rng.normal(0, 0.6, (n, F))
+    y = np.cos(2 * x[:, 0]) + 0.3 * x[:, 1] ** 3 + 0.05 * rng.normal(size=n)
+    w = rng.uniform(0.5, 2, n) if weighted else None
+    lo, hi = shard_bounds(n, world, rank)
+    eng = ChebyshevLeastSquares(D, group=dist.group.WORLD, kernels=_OracleKernels())
+    scores, r2 = eng.solve(x[lo:hi], y[lo:hi], None if w is None else w[lo:hi])
+    ref_s, ref_r = do.evaluate_degree(x, y, D, w)                 # the reference algorithm on ALL rows
+    ok = bool(np.abs(scores - ref_s).max() <= 1e-12 * ref_s.max() and np.abs(r2 - ref_r).max() <= 1e-9 * max(1, np.abs(ref_r).max()))
+    q.put((rank, ok, eng.last["rows"], eng.last["rows_local"], scores.tolist()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_sharded_degree_evaluation_gloo_world2(weighted):
+    """Rows sharded over two ranks: Gram matrices and residual sums are all-reduced, every rank gets the scores of the
+    whole data set (the kernels are replaced by their oracle, the host logic is the product's)."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_degree_worker, args=(r, 2, port, weighted, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _, _, _ in res), res
+    assert [r[2] for r in res] == [1501, 1501] and sum(r[3] for r in res) == 1501
+    assert res[0][4] == res[1][4]                                     # both ranks hold the same scores

@@ -135,8 +135,8 @@ def run_reference(a):
         vals.append(base["value"])
     v = float(np.median(vals))
     base["value"] = v
-    line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": base["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+    line = {"metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": a.gpus, "steps": len(vals), "steps_requested": a.steps,
+            "warmup": a.warmup, "ms_per_step": base["wall_s"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": workload_name(a), "note": "CPU port of the reference algorithm (the reference is "
                        "pure Python and cannot travel to the GPU box); each step = a bounded sample of the workload"},

@@ -75,8 +75,10 @@ int qkan_layer_forward_peers(qkan_layer* layer, const double* x, int64_t B, void
 int qkan_layer_forward_multicast(qkan_layer* layer, const double* x, int64_t B, void* mc_out, int64_t row_offset,
                                  void* cuda_stream);
 
-/* Same call with HOST buffers (pinned memory recommended): the batch is cut in chunks and
- * H2D copy, kernel and D2H copy of consecutive chunks overlap on three streams.
+/* Same call with HOST buffers.  Pinned (page-locked, device-mapped) buffers: zero-copy - the kernel itself streams
+ * x from host memory (TMA bulk loads over PCIe) and stores every result straight into the host buffer, so there
+ * are no staging copies and no chunk pipeline.  Pageable buffers (or QKAN_HOST_PATH=staged): the batch is cut in
+ * chunks and H2D copy, kernel and D2H copy of consecutive chunks overlap on three streams.
  * Synchronous: returns when `out` (and `amps`) are complete. */
 int qkan_layer_forward_host(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps);
 
@@ -113,7 +115,13 @@ typedef struct {
                                    mode, 1 <= D <= 16); 0: plain (cos, sin) rotations                         */
     int input_window;           /* > 0: window kernel (wide input rows) - rotation entries are built per row step
                                    from this many inputs instead of once per sample from all N                 */
+    int degree_factored;        /* 1: the D + 1 degree copies of an (a, b) block share ONE evolution through the CHEB
+                                   sequence (the state is (block) (x) |+>_deg until SELECT) and SELECT is then applied
+                                   per copy: 12 D + 4 FP instructions per (a, b) instead of (8 D + 4)(D + 1)       */
     double flops_survey;        /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)                     */
+    double flops_per_block_basis; /* round-1 accounting: every (a, b, d) block evolved on its own through the whole
+                                   sequence, (16 D + 4) flops each in the scaled form - reported so that throughput can
+                                   be compared on the old basis; equals flops_exec when degree_factored == 0      */
     double flops_exec;          /* arithmetic the kernel executes (DFMA = 2, DMUL = DADD = 1)             */
     double fp_inst_exec;        /* FP64 (FP32 for complex64) lane-instructions behind flops_exec          */
     double layout_efficiency;   /* live block slots / issued block slots (block engine)                   */

@@ -74,46 +74,57 @@ def instances():
     return out
 
 
-# block engine (default): (U, SU, NT) -> occupancy target (min CTAs per SM).
-# U = blocks per lane in registers (1 by default, 4 when shared memory limits the resident warps),
-# SU = samples per lane at a time (2 for D <= 4).  Chosen from profiles/r01_tune_block_engine_v*.jsonl.
+# block engine, generic (cos, sin) kernels (paper mode, D = 0, D > 16, very wide rows): (U, NT) -> min CTAs per SM.
+# U = blocks per lane in registers (1 by default, 4 when shared memory limits the resident warps).
 BLOCK_MINB = {
-    (4, 1, 256): 2, (4, 1, 128): 4, (4, 1, 64): 8, (4, 1, 32): 16,
-    (2, 1, 256): 3, (2, 1, 128): 6,
-    (1, 1, 256): 4, (1, 1, 128): 8, (1, 1, 64): 16, (1, 1, 32): 32,
-    (1, 2, 256): 3, (1, 2, 128): 5,
-    (1, 4, 256): 2, (1, 4, 128): 4,      # tuning variants (QKAN_BLOCK_TUNE=1:128:3:4): four samples per lane
+    (4, 256): 2, (4, 128): 4, (4, 64): 8, (4, 32): 16,
+    (1, 256): 4, (1, 128): 8, (1, 64): 16, (1, 32): 32,
 }
 DT_MAX = 16     # compile-time degree specialisations (compat mode): D = 1 .. DT_MAX
-SU2_DT_MAX = 8  # two samples per lane only pay off for shallow sequences
 
 
 def block_instances():
     out = []   # (group, amp, U, SU, MODE, NT, MINB, DT, is_default)
     for amp in ("c128", "c64", "r64"):
         for mode in (0, 1):
-            for (U, SU, NT), minb in BLOCK_MINB.items():
-                if (U == 2 and amp != "c128") or SU == 4:
-                    continue          # U = 2 is only reachable through the tuning override; SU = 4 only degree-specialised
-                out.append((f"block_{amp}_m{mode}", amp, U, SU, mode, NT, minb, 0, 1))
-        # degree-specialised kernels: compat mode, CTA sizes 256 / 128
-        for dt in range(1, DT_MAX + 1):
-            for (U, SU, NT), minb in BLOCK_MINB.items():
-                if NT not in (256, 128) or U == 2 or (SU == 2 and dt > SU2_DT_MAX) or (SU == 4 and (dt > 4 or amp != "c128")):
-                    continue
-                out.append((f"block_{amp}_d{dt}", amp, U, SU, 0, NT, minb, dt, 1))
+            for (U, NT), minb in BLOCK_MINB.items():
+                out.append((f"block_{amp}_m{mode}", amp, U, 1, mode, NT, minb, 0, 1))
     return out
 
 
-WINDOW_CTAS = ((256, 4), (256, 3))   # (NT, MINB) of the window kernels (wide input rows, scaled-rotation form, D = 2 .. DT_MAX)
+# a-major scaled-rotation kernels (qkan_amajor.cuh; the default for compat mode, 1 <= D <= DT_MAX):
+# (SU, NT) -> [(MINB, is_default)].  SU = samples per lane at a time.  Non-default entries are tuning variants
+# (QKAN_BLOCK_TUNE=1:NT:MINB:SU), built for complex128 only.
+AMAJOR = {
+    (1, 256): [(4, 1), (3, 0)],
+    (2, 256): [(4, 0), (3, 1)],
+    (4, 256): [(3, 0), (2, 1)],
+    (1, 128): [(8, 1)],
+    (2, 128): [(6, 1)],
+}
+WINDOW_CTAS = ((256, 4, 1), (256, 3, 0))   # (NT, MINB, is_default) of the window kernels (wide input rows)
+
+
+def amajor_instances():
+    out = []   # (group, amp, SU, NT, MINB, DT, is_default)
+    for amp in ("c128", "c64", "r64"):
+        for dt in range(1, DT_MAX + 1):
+            for (SU, NT), variants in AMAJOR.items():
+                for (minb, dflt) in variants:
+                    if not dflt and amp != "c128":
+                        continue
+                    out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
+    return out
 
 
 def window_instances():
-    out = []   # (group, amp, NT, MINB, DT)
+    out = []   # (group, amp, NT, MINB, DT, is_default)
     for amp in ("c128", "c64", "r64"):
         for dt in range(1, DT_MAX + 1):
-            for (nt, minb) in WINDOW_CTAS:
-                out.append((f"block_{amp}_d{dt}", amp, nt, minb, dt))
+            for (nt, minb, dflt) in WINDOW_CTAS:
+                if not dflt and amp != "c128":
+                    continue
+                out.append((f"amajor_{amp}_d{dt}", amp, nt, minb, dt, dflt))
     return out
 
 
@@ -134,6 +145,9 @@ def main():
     bgroups = {}
     for it in binst:
         bgroups.setdefault(it[0], []).append(it)
+    agroups = {}
+    for it in amajor_instances():
+        agroups.setdefault(it[0], []).append(it)
     wgroups = {}
     for it in window_instances():
         wgroups.setdefault(it[0], []).append(it)
@@ -165,9 +179,21 @@ def main():
         for (_, amp, U, SU, MODE, NT, MINB, DT, dflt) in items:
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_block_info<{A}, {R}, {U}, {SU}, {MODE}, {NT}, {MINB}, {DT}>({dflt}));\n")
-        for (_, amp, NT, MINB, DT) in wgroups.get(g, []):
+        fh.write("}\n")
+        wanted.add(f"inst_{g}.cu")
+        write_if_changed(os.path.join(d, f"inst_{g}.cu"), fh.getvalue())
+    for g, items in sorted(agroups.items()):
+        bnames.append(g)
+        fh = io.StringIO()
+        fh.write("// generated by gen_instances.py - do not edit\n")
+        fh.write('#include "../qkan_amajor.cuh"\n#include <vector>\nusing namespace qkan;\n')
+        fh.write(f"void qkan_register_{g}(std::vector<BlockKernelInfo>& reg) {{\n")
+        for (_, amp, SU, NT, MINB, DT, dflt) in items:
             A, R, _sz = AMPS[amp]
-            fh.write(f"    reg.push_back(make_block_window_info<{A}, {R}, {NT}, {MINB}, {DT}>());\n")
+            fh.write(f"    reg.push_back(make_amajor_info<{A}, {R}, {SU}, {NT}, {MINB}, {DT}>({dflt}));\n")
+        for (_, amp, NT, MINB, DT, dflt) in wgroups.get(g, []):
+            A, R, _sz = AMPS[amp]
+            fh.write(f"    reg.push_back(make_amajor_window_info<{A}, {R}, {NT}, {MINB}, {DT}>({dflt}));\n")
         fh.write("}\n")
         wanted.add(f"inst_{g}.cu")
         write_if_changed(os.path.join(d, f"inst_{g}.cu"), fh.getvalue())
@@ -191,7 +217,7 @@ def main():
             fh.write(f"    qkan_register_{g}(reg);\n")
         fh.write("}\n")
         write_if_changed(os.path.join(HERE, "qkan_instances.h"), fh.getvalue())
-    print(f"{len(inst)} staged + {len(binst)} block instances in {len(names) + len(bnames)} translation units")
+    print(f"{len(inst)} staged + {len(binst)} generic block + {len(amajor_instances())} a-major + {len(window_instances())} window instances in {len(names) + len(bnames)} translation units")
 
 
 if __name__ == "__main__":

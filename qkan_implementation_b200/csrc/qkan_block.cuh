@@ -288,13 +288,9 @@ QK_HD A evolve_blocks(const A (&init)[4], const R (&cx)[U], const R (&sx)[U], co
 // folding the 1/sqrt(2) of every Hadamard into the read-out scale; every amplitude of every block
 // is still evolved through every gate.  |t| <= 1 bounds the un-normalised state by 2^(D/2), which
 // is why the form is used for the degree-specialised kernels (D <= 16) only.
-#ifndef QKAN_TAN_FORM
-#define QKAN_TAN_FORM 1
-#endif
 constexpr int TAN_MIN_DT = 1;        // D = 1: no full pass to save, but the pruned pass + SELECT are 12 instead of 14 instructions
-// U = 1 only: the U = 4 kernels serve wide input rows, where the cs tile (24 instead of 16 bytes per input
-// element) already limits the resident warps (measured on N784 K10 D5: 3.97 -> 2.96 M samples/s with triples)
-constexpr bool use_tan_form(int mode, int dt, int U) { return QKAN_TAN_FORM && mode == 0 && dt >= TAN_MIN_DT && U == 1; }
+constexpr int TAN_MAX_DT = 16;       // |t| <= 1 bounds the un-normalised state by 2^(D/2)
+// (the kernels that use this form are in qkan_amajor.cuh)
 
 template <typename R> struct TanEntry { R t, al, be; };
 
@@ -429,9 +425,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     const int SPC = p.SPC;                                   // samples in flight per CTA
     const int tile = p.tile;                                 // samples per x tile
     const int RB = p.row_bytes;                              // cs row stride: N entries + the dummy (+ padding)
-    // scaled-rotation form: a sample's cs row holds (t, alpha, beta) triples instead of (cos, sin) pairs
-    constexpr bool TAN = use_tan_form(MODE, DT, U);
-    constexpr size_t ENTB = TAN ? sizeof(TanEntry<R>) : sizeof(CS<R>);   // bytes per entry
+    constexpr size_t ENTB = sizeof(CS<R>);                   // bytes per entry
     // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (rotation entries of the current tile, plus
     // SU - 1 sub-iterations of slack rows: the idle slots of a ragged tile read past its last row) | mbar[2]
     const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
@@ -463,13 +457,9 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
     }
     // the dummy entries never change
     for (int i = tid; i < tile; i += NT) {
-        if constexpr (TAN) {
-            *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + p.N * ENTB) = tan_entry<R>(R(0), DT);
-        } else {
-            CS<R> e;
-            e.c = R(0); e.s = R(1);
-            *reinterpret_cast<CS<R>*>(cs + (size_t)i * RB + p.N * ENTB) = e;
-        }
+        CS<R> e;
+        e.c = R(0); e.s = R(1);
+        *reinterpret_cast<CS<R>*>(cs + (size_t)i * RB + p.N * ENTB) = e;
     }
     __syncthreads();
 
@@ -558,14 +548,10 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                 const double v = xs[e];
                 if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
                 const R c = clip_unit<R>(v);
-                if constexpr (TAN) {
-                    *reinterpret_cast<TanEntry<R>*>(cs + (size_t)row * RB + n * ENTB) = tan_entry<R>(c, DT);
-                } else {
-                    CS<R> en;
-                    en.c = c;
-                    en.s = qk_sqrt((R(1) - c) * (R(1) + c));
-                    *reinterpret_cast<CS<R>*>(cs + (size_t)row * RB + n * ENTB) = en;
-                }
+                CS<R> en;
+                en.c = c;
+                en.s = qk_sqrt((R(1) - c) * (R(1) + c));
+                *reinterpret_cast<CS<R>*>(cs + (size_t)row * RB + n * ENTB) = en;
                 n += pre_dn;
                 row += pre_dr;
                 if (n >= p.N) { n -= p.N; ++row; }
@@ -609,19 +595,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
                     xp += (size_t)U * G;
                     QK_UNROLL
                     for (int u = 0; u < U; ++u) { qn[u] = cp[(size_t)u * G]; xn[u] = xp[(size_t)u * G]; }
-                    if constexpr (TAN) {
-                        R tx[SU][U], ax[SU][U], bx[SU][U];
-                        QK_UNROLL
-                        for (int j = 0; j < SU; ++j) {
-                            QK_UNROLL
-                            for (int u = 0; u < U; ++u) {
-                                const TanEntry<R>* e = reinterpret_cast<const TanEntry<R>*>(row[j] + xoff[u]);
-                                tx[j][u] = e->t; ax[j][u] = e->al; bx[j][u] = e->be;
-                            }
-                        }
-                        QK_UNROLL
-                        for (int j = 0; j < SU; ++j) evolve_blocks_tan<A, R, U, DT>(init, tx[j], ax[j], bx[j], cw, sw, acc[j]);
-                    } else {
+                    {
                         R cx[SU][U], sx[SU][U];
                         QK_UNROLL
                         for (int j = 0; j < SU; ++j) {
@@ -676,114 +650,6 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
 }
 
 
-// Window kernel: wide input rows (N784 K10: 6.3 KB of x, 19 KB of rotation triples per sample).  The entries of
-// a sample are built per ROW STEP from the step's input window (block_window) instead of once per sample, so a
-// CTA keeps tile * (W + 1) triples instead of tile * (N + 1) and shared memory no longer limits the resident
-// warps.  Scaled-rotation form, one block per lane at a time (U = 1, SU = 1); x is read straight from global
-// memory (each input is read once per row step that uses it: twice at most, at window boundaries).
-template <class A, typename R, int NT, int MINB, int DT>
-__global__ void __launch_bounds__(NT, MINB) qkan_block_window_kernel(const BlockParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int G = p.G, G_r = p.G_r;
-    const int SPC = p.SPC, tile = p.tile, RB = p.row_bytes, W = p.window;
-    constexpr size_t ENTB = sizeof(TanEntry<R>);
-    char* cs = reinterpret_cast<char*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int g = tid & (G - 1);
-    const int r = g & (G_r - 1);
-    const int k = g >> p.g_r_log2;
-    const int slot = tid >> (p.g_r_log2 + p.g_k_log2);
-    const CS<R>* __restrict__ cstab = reinterpret_cast<const CS<R>*>(p.cstab);
-    const int* __restrict__ xotab = p.xotab;
-
-    for (int i = tid; i < tile; i += NT)                      // the dummy entries never change
-        *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + W * ENTB) = tan_entry<R>(R(0), DT);
-    A init[4];
-    QK_UNROLL
-    for (int q = 0; q < 4; ++q) {
-        init[q].re = (R)p.init[2 * q];
-        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
-    }
-    QK_UNROLL
-    for (int q = 0; q < 4; ++q) {
-        keep_in_register(init[q].re);
-        if constexpr (A::is_complex) keep_in_register(init[q].im);
-    }
-    const long long n_it = (p.B + tile - 1) / tile;
-    const size_t step_slots = (size_t)p.passes * G;           // table entries of one row step
-
-    for (long long it = blockIdx.x; it < n_it; it += gridDim.x) {
-        const long long s0 = it * tile;
-        const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
-        const int nsub = (nsamp + SPC - 1) / SPC;
-        int prev_hi = -1;
-        for (int bi = 0; bi < p.brows; ++bi) {
-            int lo, len;
-            block_window(p.N, p.K, p.g_k_log2, bi, &lo, &len);
-            __syncthreads();                                  // the previous row step's entries are consumed
-            // pre-pass over the window of every sample of the tile (flat walk, no division in the loop): range count
-            // (ChebyshevStep.py:46-49; an input shared by two windows is counted once), clip (:52), entry
-            unsigned bad = 0;
-            {
-                const int n_in = nsamp * len;
-                int row = tid / len, j = tid - row * len;
-                const int dr = NT / len, dj = NT - dr * len;
-                const double* xw = p.x + s0 * p.N + lo;
-                for (int e = tid; e < n_in; e += NT) {
-                    const double v = xw[(size_t)row * p.N + j];
-                    if (lo + j > prev_hi && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
-                    *reinterpret_cast<TanEntry<R>*>(cs + (size_t)row * RB + j * ENTB) = tan_entry<R>(clip_unit<R>(v), DT);
-                    j += dj;
-                    row += dr;
-                    if (j >= len) { j -= len; ++row; }
-                }
-            }
-            prev_hi = lo + len - 1;
-            if (bad) atomicAdd(p.oor, (unsigned long long)bad);
-            __syncthreads();
-
-            const int b = (bi << p.g_k_log2) + k;
-            const CS<R>* cp0 = cstab + (size_t)bi * step_slots + g;
-            const int* xp0 = xotab + (size_t)bi * step_slots + g;
-            const CS<R> q0 = cp0[0];
-            const int x0 = xp0[0];
-            int ls = slot;
-            for (int si = 0; si < nsub; ++si, ls += SPC) {
-                const char* row = cs + (size_t)ls * RB;       // idle slots of a ragged tile evolve a stale row; nothing is stored
-                const CS<R>* cp = cp0;
-                const int* xp = xp0;
-                CS<R> qn = q0;
-                int xn = x0;
-                A acc;
-                set_amp(acc, 0.0);
-                for (int pi = 0; pi < p.passes; ++pi) {
-                    const R cw[1] = {qn.c}, sw[1] = {qn.s};
-                    const TanEntry<R>* e = reinterpret_cast<const TanEntry<R>*>(row + xn);
-                    cp += G;
-                    xp += G;
-                    qn = cp[0];                               // next pass (the tables end with one pass of padding slots)
-                    xn = xp[0];
-                    const R t[1] = {e->t}, al[1] = {e->al}, be[1] = {e->be};
-                    evolve_blocks_tan<A, R, 1, DT>(init, t, al, be, cw, sw, acc);
-                }
-                // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
-                for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc, shfl_xor_amp(acc, m));
-                if (ls < nsamp && r == 0 && b < p.K) {
-                    const long long o = (p.row0 + s0 + ls) * p.K + b;
-                    store_result(p, o, (double)acc.re * p.out_scale);
-                    if (p.amps) {
-                        Cplx<R> z;
-                        z.re = (R)((double)acc.re * p.amp_scale);
-                        if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
-                        else z.im = R(0);
-                        reinterpret_cast<Cplx<R>*>(p.amps)[(s0 + ls) * p.K + b] = z;
-                    }
-                }
-            }
-        }
-    }
-}
-
 template <typename R>
 __global__ void qkan_prepare_block_tables_kernel(const double* W, int N, int K, int D, int U, int passes, int g_r_log2,
                                                  int g_k_log2, int paper, int x_entry_bytes, int window, long long slots_total,
@@ -802,8 +668,9 @@ struct BlockKernelInfo {
     int amp, mode, U, NT, MINB;
     int SU;                     // samples per lane at a time
     int DT;                     // 0 = any D (run-time loop), else only for D == DT
-    int tan;                    // scaled-rotation form (use_tan_form): cs rows hold (t, alpha, beta) triples
+    int tan;                    // scaled-rotation form: cs rows hold (t, alpha, beta) triples (qkan_amajor.cuh)
     int window;                 // window kernel (wide input rows): entries are built per row step
+    int amajor;                 // a-major tables (qkan_amajor.cuh): D + 1 SELECT entries per (row step, pass, lane)
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
@@ -813,12 +680,7 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
     auto kern = qkan_block_kernel<A, R, U, SU, MODE, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
-    constexpr bool TAN = use_tan_form(MODE, DT, U);
-    p.row_bytes = TAN ? tan_row_words(p.N, G, (int)sizeof(R)) * (int)sizeof(R)
-                      : cs_row_stride(p.N, G, (int)sizeof(CS<R>)) * (int)sizeof(CS<R>);
-    if (const char* e = getenv("QKAN_BLOCK_ROW_WORDS")) {      // tuning aid (scaled-rotation rows only)
-        if (TAN && atoi(e) >= 3 * (p.N + 1)) p.row_bytes = atoi(e) * (int)sizeof(R);
-    }
+    p.row_bytes = cs_row_stride(p.N, G, (int)sizeof(CS<R>)) * (int)sizeof(CS<R>);
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
     // halve the resident warps; the per-tile compute is long, so the pre-pass reads global memory directly
     p.direct_x = ((size_t)SPC * p.N * 16 > 16 * 1024) ? 1 : 0;
@@ -829,7 +691,7 @@ cudaError_t launch_block_impl(const BlockParams& p0, int G, int sm_count, cudaSt
         return xs + cs + 16;
     };
     int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile ...
-    const int sub_cs = (int)((TAN ? 49152 : 24576) / ((size_t)SPC * p.row_bytes));   // ... and at most 24 KiB of rotation pairs (48 KiB of triples)
+    const int sub_cs = (int)(24576 / ((size_t)SPC * p.row_bytes));   // ... and at most 24 KiB of rotation pairs
     if (sub > sub_cs) sub = sub_cs;
     if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
@@ -885,52 +747,8 @@ BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = use_tan_form(MODE, DT, U) ? 1 : 0;
-    k.window = 0;
+    k.tan = 0; k.window = 0; k.amajor = 0;
     k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
-    return k;
-}
-template <class A, typename R, int NT, int MINB, int DT>
-cudaError_t launch_block_window(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    if (p0.D != DT || p0.window < 1) return cudaErrorInvalidValue;
-    auto kern = qkan_block_window_kernel<A, R, NT, MINB, DT>;
-    BlockParams p = p0;
-    const int SPC = NT / G;
-    p.row_bytes = tan_row_words(p.window, G, (int)sizeof(R)) * (int)sizeof(R);
-    int sub = (int)(32768 / ((size_t)SPC * p.row_bytes));      // about 32 KiB of rotation triples per CTA
-    if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
-    if (sub > 32) sub = 32;
-    if (sub < 1) sub = 1;
-    auto smem_for = [&](int sb) { return (size_t)SPC * sb * p.row_bytes; };
-    if (smem_for(sub) > 200 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(sub));
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_for(sub));
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const long long resident = (long long)sm_count * per_sm;
-    while (sub > 1 && (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub) < 4 * resident) sub >>= 1;
-    const long long n_it = (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub);
-    long long grid = resident < n_it ? resident : n_it;
-    if (grid < 1) grid = 1;
-    p.sub = sub;
-    p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
-    p.SPC = SPC; p.tile = SPC * sub;
-    p.tma_ok = 0; p.direct_x = 1; p.s_tot = -1;
-    if (grid_out) *grid_out = (int)grid;
-    if (smem_out) *smem_out = (int)smem_for(sub);
-    kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
-    return cudaGetLastError();
-}
-template <class A, typename R, int NT, int MINB, int DT>
-BlockKernelInfo make_block_window_info() {
-    BlockKernelInfo k;
-    k.amp = AmpId<A>::v;
-    k.mode = 0; k.U = 1; k.SU = 1; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = 1;
-    k.tan = 1;
-    k.window = 1;
-    k.launch = &launch_block_window<A, R, NT, MINB, DT>;
     return k;
 }
 #endif  // __CUDACC__

@@ -2,6 +2,7 @@
 // device and host-buffer forward, FMA peak microbenchmark.
 #include "qkan_kernel.cuh"
 #include "qkan_block.cuh"
+#include "qkan_amajor.cuh"
 #include "qkan_instances.h"
 #include "../../include/qkan_b200.h"
 
@@ -102,13 +103,62 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB:SU" (0 = any)
         int fU = 0, fNT = 0, fMINB = 0, fSU = 0;
         if (tune) sscanf(tune, "%d:%d:%d:%d", &fU, &fNT, &fMINB, &fSU);
-        // two samples per lane share every table entry: measured +4..+15 % for D <= 4 (fixed per-block overhead
-        // matters there), slower for deep sequences (profiles/r01_tune_block_engine_v12_su2.jsonl)
-        const int want_SU = fSU ? fSU : (max_degree <= 4 ? 2 : 1);
-        // the (cos, sin) pair, or the (t, alpha, beta) triple of the scaled-rotation kernels (wide rows skip the raw-x staging)
-        const bool tan_dt = max_degree <= 16 && !getenv("QKAN_BLOCK_NO_DT");
-        // 256-thread CTAs first (measured best or equal for SU = 1 and, with the scaled-rotation kernels, SU = 2:
-        // N4 K4 D3 0.174 -> 0.164 ms, gpurun_out/ab_c2.log)
+        const size_t rsz = amp_real_size(dtype);
+        // ---- a-major scaled-rotation kernels (qkan_amajor.cuh): compat mode, 1 <= D <= 16
+        const bool amajor_ok = mode == QKAN_MODE_COMPAT && max_degree >= TAN_MIN_DT && max_degree <= TAN_MAX_DT &&
+                               fU <= 1 && !getenv("QKAN_BLOCK_NO_DT");
+        // two samples per lane share every SELECT entry and the per-pass bookkeeping: pays for shallow sequences
+        const int want_SU = fSU ? fSU : 2;
+        auto find_amajor = [&](int NT, int SU, bool window_kernel) -> const BlockKernelInfo* {
+            for (const BlockKernelInfo& k : block_registry()) {
+                if (!k.amajor || (k.window != 0) != window_kernel || k.amp != dtype || k.DT != max_degree || k.NT != NT) continue;
+                if (!window_kernel && k.SU != SU) continue;
+                if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
+                return &k;
+            }
+            return nullptr;
+        };
+        // resident warps per SM that the shared memory of one CTA allows (registers cap it at 32 / 24)
+        auto warps_for = [](size_t smem, int NT) { return (int)((220 * 1024 / (smem + 1024)) * (size_t)(NT / 32)); };
+        // pass 0 wants >= 24 resident warps (the FP64 pipe needs them to stay busy), pass 1 takes whatever launches
+        for (int pass = 0; pass < 2 && amajor_ok && !bbest; ++pass) {
+            const int NTs[2] = {256, 128};
+            for (int ni = 0; ni < 2 && !bbest && !getenv("QKAN_BLOCK_FORCE_WINDOW"); ++ni) {
+                const int NT = NTs[ni];
+                if (fNT && NT != fNT) continue;
+                for (int min_g = 0; min_g <= 5 && !bbest; ++min_g) {
+                    const BlockLayout cand = plan_amajor_layout(N, K, min_g);
+                    const int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
+                    if (G < (1 << min_g) || G > NT) continue;
+                    const int SPC = NT / G;
+                    const int row_bytes = tan_row_words(N, G, (int)rsz) * (int)rsz;
+                    for (int SU = want_SU; SU >= 1 && !bbest; --SU) {
+                        const size_t smem = amajor_smem_bytes(N, SPC, row_bytes, SU, SU);     // smallest tile the launch can use
+                        if (smem > AMAJOR_SMEM_CAP || (pass == 0 && warps_for(smem, NT) < 24)) continue;
+                        const BlockKernelInfo* k = find_amajor(NT, SU, false);
+                        if (k) { bbest = k; lay = cand; }
+                    }
+                }
+            }
+            // wide input rows: the window kernel builds the triples per row step from the step's input window
+            // (N784 K10 D5).  Narrowest lane group whose window tile leaves room for four (else three) 256-thread
+            // CTAs per SM; rows in parallel capped first at 1, then 2, ... (the window grows with them)
+            if (fNT && fNT != 256) continue;
+            if (getenv("QKAN_BLOCK_NO_WINDOW")) continue;
+            for (int want = pass == 0 ? 32 : 8; want >= (pass == 0 ? 24 : 8) && !bbest; want -= 8)
+            for (int gkm = 0; gkm <= 5 && !bbest; ++gkm)
+            for (int mg = 0; mg <= 5 && !bbest; ++mg) {
+                const BlockLayout c = plan_amajor_layout(N, K, mg, gkm);
+                const int G = 1 << (c.g_r_log2 + c.g_k_log2);
+                if (G < (1 << mg) || c.efficiency < 0.9) continue;
+                const int W = block_window_max(N, K, c.g_k_log2, c.brows);
+                const size_t win_cs = amajor_window_smem_bytes(256 / G, tan_row_words(W, G, (int)rsz) * (int)rsz, 1);
+                if (win_cs > AMAJOR_SMEM_CAP || warps_for(win_cs, 256) < want) continue;
+                const BlockKernelInfo* k = find_amajor(256, 1, true);
+                if (k) { bbest = k; lay = c; window = W; }
+            }
+        }
+        // ---- generic (cos, sin) kernels: paper mode, D = 0, D > 16, or rows too wide for the above
         const int NTs[4] = {256, 128, 64, 32};
         for (int ni = 0; ni < 4 && !bbest; ++ni) {
             const int NT = NTs[ni];
@@ -117,10 +167,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
                 int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                 if (G < (1 << min_g) || G > NT) continue;
-                auto cs_bytes_for = [&](int U) {
-                    const size_t per_x = (use_tan_form(mode, tan_dt ? max_degree : 0, U) ? 3 : 2) * amp_real_size(dtype);
-                    return (size_t)(NT / G) * (N + 1) * per_x;
-                };
+                auto cs_bytes_for = [&](int) { return (size_t)(NT / G) * (N + 1) * 2 * rsz; };
                 // wide input rows: shared memory limits the resident warps (< 24 per SM), so keep four blocks
                 // per lane in flight instead of one (measured on N784 K10 D5: 3.7 -> 4.0 M samples/s)
                 if (!fU && (220 * 1024 / (cs_bytes_for(cand.U) + 1024)) * (size_t)(NT / 32) < 24) {
@@ -128,48 +175,20 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                     const int Gw = 1 << (wide.g_r_log2 + wide.g_k_log2);
                     if (Gw == G) cand = wide;
                 }
+                // the launch adds at most 16 KiB of raw-x staging (wider tiles read x directly) to one SPC-row cs tile
                 if (cs_bytes_for(cand.U) > 72 * 1024) continue;
-                const BlockKernelInfo* generic = nullptr;
                 for (const BlockKernelInfo& k : block_registry()) {
-                    if (k.window || k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT) continue;
-                    if (k.SU != ((cand.U == 1 && (NT == 256 || NT == 128)) ? want_SU : 1)) continue;
+                    if (k.amajor || k.window || k.amp != dtype || k.mode != mode || k.U != cand.U || k.NT != NT || k.DT != 0) continue;
                     if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
-                    if (k.DT == max_degree && !getenv("QKAN_BLOCK_NO_DT")) { bbest = &k; break; }   // degree-specialised
-                    if (k.DT == 0 && !generic) generic = &k;
+                    bbest = &k;
+                    break;
                 }
-                if (!bbest) bbest = generic;
                 if (bbest) lay = cand;
             }
         }
-        // wide input rows (the main path found nothing, or had to fall back to the U = 4 (cos, sin) kernels because
-        // the rotation entries of whole input rows left room for < 24 warps per SM): the window kernel builds the
-        // entries per row step from the step's input window (N784 K10 D5: 4.0 -> 6.3 M samples/s).  Scaled-rotation
-        // form only (compat mode, 1 <= D <= 16).
-        if (use_tan_form(mode, tan_dt ? max_degree : 0, 1) && fU <= 1 && !getenv("QKAN_BLOCK_NO_WINDOW")) {
-            const bool bound = !bbest || bbest->U == 4;
-            // narrowest lane group whose window tile leaves room for four (else three) 256-thread CTAs per SM
-            // (rows in parallel capped first at 1, then 2, ...: the window grows with them)
-            for (int want = 32; want >= 24 && bound && !window; want -= 8)
-            for (int gkm = 0; gkm <= 5 && !window; ++gkm)
-            for (int mg = 0; mg <= 5 && !window; ++mg) {
-                const BlockLayout c = plan_block_layout(N, K, max_degree, mg, 1, gkm);
-                const int G = 1 << (c.g_r_log2 + c.g_k_log2);
-                if (G < (1 << mg) || c.efficiency < 0.9) continue;
-                const int W = block_window_max(N, K, c.g_k_log2, c.brows);
-                const size_t win_cs = (size_t)(256 / G) * (W + 1) * 3 * amp_real_size(dtype);
-                if ((220 * 1024 / (win_cs + 1024)) * 8 < (size_t)want) continue;
-                for (const BlockKernelInfo& k : block_registry()) {
-                    if (!k.window || k.amp != dtype || k.DT != max_degree) continue;
-                    if (fNT && k.NT != fNT) continue;
-                    if (fMINB && k.MINB != fMINB) continue;
-                    bbest = &k; lay = c; window = W;
-                    break;
-                }
-            }
-        }
         if (getenv("QKAN_DEBUG_SELECT") && bbest)
-            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
-                    N, K, max_degree, dtype, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
+            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> amajor=%d U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
+                    N, K, max_degree, dtype, bbest->amajor, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
                     lay.g_r_log2, lay.g_k_log2, lay.passes, lay.brows);
         if (!bbest) {
             char buf[160];
@@ -217,7 +236,9 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const size_t G = (size_t)1 << (l->lay.g_r_log2 + l->lay.g_k_log2);
         // (+ 8 more, never read: the window kernel's L1 prefetches run WINDOW_PREFETCH passes ahead)
         const size_t slots = ((size_t)l->lay.brows * l->lay.passes + 1 + 8) * l->lay.U * G;
-        e = cudaMalloc(&l->wtab, slots * 2 * amp_real_size(dtype));
+        // a-major tables: D + 1 SELECT entries per (row step, pass, lane) step
+        const size_t per_slot = l->bkern->amajor ? (size_t)(max_degree + 1) : 1;
+        e = cudaMalloc(&l->wtab, slots * per_slot * 2 * amp_real_size(dtype));
         if (e == cudaSuccess) e = cudaMalloc(&l->xidx, slots * sizeof(int));
     } else {
         e = cudaMalloc(&l->wtab, (nab << L) * 2 * amp_real_size(dtype));
@@ -257,7 +278,18 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
                            stream));
     const double* Wd = l->W_dev;
     CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
-    if (l->engine == 0) {
+    if (l->engine == 0 && l->bkern->amajor) {
+        const long long steps = amajor_steps(l->lay);
+        const unsigned nt = 128, nb = (unsigned)((steps + nt - 1) / nt);
+        if (l->dtype == QKAN_COMPLEX64)
+            qkan_prepare_amajor_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
+                                                                            l->lay.g_r_log2, l->lay.g_k_log2, 12, l->window, steps,
+                                                                            (CS<float>*)l->wtab, l->xidx, l->counters + 1);
+        else
+            qkan_prepare_amajor_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
+                                                                             l->lay.g_r_log2, l->lay.g_k_log2, 24, l->window, steps,
+                                                                             (CS<double>*)l->wtab, l->xidx, l->counters + 1);
+    } else if (l->engine == 0) {
         const long long G = 1ll << (l->lay.g_r_log2 + l->lay.g_k_log2);
         // one extra row step of slots decodes to b >= K, i.e. padding: covers the prefetch overrun
         const long long slots = ((long long)l->lay.brows * l->lay.passes + 1) * l->lay.U * G;
@@ -266,12 +298,12 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_block_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                           l->bkern->tan ? 12 : 8, l->window, slots,
+                                                                           8, 0, slots,
                                                                            (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_block_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.U, l->lay.passes,
                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->mode,
-                                                                            l->bkern->tan ? 24 : 16, l->window, slots,
+                                                                            16, 0, slots,
                                                                             (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else {
     const unsigned nab = 1u << (l->NA + l->NB);
@@ -514,11 +546,16 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         info->fp_inst_exec = cf * (double)info->blocks * (l->D > 0 ? 16.0 * Dd - 2.0 : 6.0);
         info->scaled_rotations = k.tan;
         info->input_window = l->window;
-        if (k.tan) {
-            // scaled-rotation form (evolve_blocks_tan): D-1 full passes of 8 FMA, the pruned last pass
-            // alpha u + beta v (4 MUL + 4 FMA), SELECT fused with the read-out sum (4 FMA)
-            info->flops_exec = cf * (double)info->blocks * (16.0 * Dd + 4.0);
-            info->fp_inst_exec = cf * (double)info->blocks * (8.0 * Dd + 4.0);
+        info->flops_per_block_basis = info->flops_exec;
+        if (k.amajor) {
+            // a-major scaled-rotation kernels (amajor_blocks): per (a, b) ONE evolution of the block state - D-1 full
+            // passes of 8 FMA and the pruned last pass alpha u + beta v (4 MUL + 4 FMA) - then per degree copy the
+            // SELECT rotation fused with the read-out sum (4 FMA)
+            const double ab = (double)l->N * l->K;
+            info->degree_factored = 1;
+            info->flops_exec = cf * ab * (16.0 * (Dd - 1.0) + 12.0 + 8.0 * (Dd + 1.0));
+            info->fp_inst_exec = cf * ab * (8.0 * Dd + 4.0 * (Dd + 1.0));
+            info->flops_per_block_basis = cf * (double)info->blocks * (16.0 * Dd + 4.0);
         }
         info->layout_efficiency = l->lay.efficiency;
     } else {

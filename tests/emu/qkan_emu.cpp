@@ -5,6 +5,7 @@
 // test-suite check the compile-time plans, swizzle and read-out against the oracle.
 #include "../../qkan_implementation_b200/csrc/qkan_core.cuh"
 #include "../../qkan_implementation_b200/csrc/qkan_block.cuh"
+#include "../../qkan_implementation_b200/csrc/qkan_amajor.cuh"
 #include <vector>
 #include <cstring>
 #include <cstdio>
@@ -121,8 +122,7 @@ template <class A, typename R, int U> struct TanRun<A, R, U, 0> {
 // tan == 2: the window kernel's tables and per-row-step input windows (U = 1 layouts only)
 template <class A, typename R, int U, int MODE>
 int emu_block(const double* x, const double* W, long long B, int N, int K, int D, int min_g, int tan, double* out, double* amps) {
-    if (tan && (MODE != 0 || D < TAN_MIN_DT || D > 16)) return -4;
-    if (tan == 2 && U != 1) return -5;
+    if (tan) return -4;              // the scaled-rotation kernels are a-major now: emu_amajor below
     const BlockLayout lay = plan_block_layout(N, K, D, min_g);
     if (lay.U != U) return -3;
     const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
@@ -208,6 +208,100 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
     }
     return 0;
 }
+
+// ---- a-major kernels (qkan_amajor.cuh): planner, tables, per-(a, b) evolution and read-out, lane by lane
+template <class A, typename R, int DT> struct AmajorRun {
+    static void go(int D, const A (&init)[4], const TanEntry<R> (&e)[1], const CS<R>* wp, A (&acc)[1]) {
+        if (D == DT) amajor_blocks<A, R, 1, DT>(init, e, wp, acc);
+        else AmajorRun<A, R, DT - 1>::go(D, init, e, wp, acc);
+    }
+};
+template <class A, typename R> struct AmajorRun<A, R, 0> {
+    static void go(int, const A (&)[4], const TanEntry<R> (&)[1], const CS<R>*, A (&)[1]) {}
+};
+
+// window != 0: the window kernel's tables and per-row-step input windows
+template <class A, typename R>
+int emu_amajor(const double* x, const double* W, long long B, int N, int K, int D, int min_g, int max_gk, int window_mode,
+               double* out, double* amps) {
+    if (D < TAN_MIN_DT || D > TAN_MAX_DT) return -4;
+    const BlockLayout lay = plan_amajor_layout(N, K, min_g, max_gk);
+    const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
+    if (G < (1 << min_g)) return -3;
+    const long long steps = amajor_steps(lay);
+    const int window = window_mode ? block_window_max(N, K, lay.g_k_log2, lay.brows) : 0;
+    std::vector<CS<R>> wtab((size_t)steps * (D + 1));
+    std::vector<int> xotab(steps);
+    for (long long e = 0; e < steps; ++e)
+        fill_amajor_step<R>(e, W, N, K, D, lay.passes, lay.brows, lay.g_r_log2, lay.g_k_log2, wtab.data(), xotab.data(),
+                            (int)sizeof(TanEntry<R>), window);
+    int NA = 0, NB = 0, L = 0;
+    while ((1 << NA) < N) ++NA;
+    while ((1 << NB) < K) ++NB;
+    while ((1 << L) < D + 1) ++L;
+    const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    for (long long s = 0; s < B; ++s) {
+        std::vector<TanEntry<R>> cst((size_t)N + 1);
+        for (int n = 0; n <= N; ++n) cst[n] = tan_entry<R>(n < N ? clip_unit<R>(x[s * N + n]) : R(0), D);
+        for (int bi = 0; bi < lay.brows; ++bi) {
+            std::vector<TanEntry<R>> row = cst;
+            if (window) {                                    // the row step's window of the input row, dummy at index `window`
+                int lo, len;
+                block_window(N, K, lay.g_k_log2, bi, &lo, &len);
+                if (len > window) return -6;
+                row.assign((size_t)window + 1, TanEntry<R>{R(7), R(7), R(7)});   // stale entries must never be read
+                for (int j = 0; j < len; ++j) row[j] = cst[lo + j];
+                row[window] = cst[N];
+            }
+            for (int k = 0; k < G_k; ++k) {
+                const int b = bi * G_k + k;
+                std::vector<A> acc(G_r);
+                for (int r = 0; r < G_r; ++r) {
+                    A a1[1];
+                    set_amp(a1[0], 0.0);
+                    const int g = k * G_r + r;
+                    for (int pi = 0; pi < lay.passes; ++pi) {
+                        const size_t st = ((size_t)bi * lay.passes + pi) * G + g;
+                        TanEntry<R> e[1];
+                        e[0] = *reinterpret_cast<const TanEntry<R>*>(reinterpret_cast<const char*>(row.data()) + xotab[st]);
+                        A init[4];
+                        for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
+                        AmajorRun<A, R, 16>::go(D, init, e, wtab.data() + st * (D + 1), a1);
+                    }
+                    acc[r] = a1[0];
+                }
+                for (int m = G_r >> 1; m >= 1; m >>= 1) {
+                    std::vector<A> nxt(acc);
+                    for (int r = 0; r < G_r; ++r) add_amp(nxt[r], acc[r ^ m]);
+                    acc = nxt;
+                }
+                if (b < K) {
+                    out[s * K + b] = (double)acc[0].re / ((double)N * (D + 1));
+                    if (amps) {
+                        amps[2 * (s * K + b)] = (double)acc[0].re * amp_scale;
+                        if constexpr (A::is_complex) amps[2 * (s * K + b) + 1] = (double)acc[0].im * amp_scale;
+                        else amps[2 * (s * K + b) + 1] = 0.0;
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" int qkan_emu_amajor_forward(int amp, int min_g, int max_gk, int window_mode, const double* x, const double* W,
+                                       long long B, int N, int K, int D, double* out, double* amps) {
+    if (amp == 0) return emu_amajor<Cplx<double>, double>(x, W, B, N, K, D, min_g, max_gk, window_mode, out, amps);
+    if (amp == 1) return emu_amajor<Cplx<float>, float>(x, W, B, N, K, D, min_g, max_gk, window_mode, out, amps);
+    if (amp == 2) return emu_amajor<Real<double>, double>(x, W, B, N, K, D, min_g, max_gk, window_mode, out, amps);
+    return -2;
+}
+extern "C" void qkan_emu_amajor_layout(int N, int K, int min_g, int max_gk, int* out4, double* eff) {
+    const BlockLayout l = plan_amajor_layout(N, K, min_g, max_gk);
+    out4[0] = l.g_r_log2; out4[1] = l.g_k_log2; out4[2] = l.passes; out4[3] = l.brows;
+    *eff = l.efficiency;
+}
+extern "C" long long qkan_emu_amajor_smem(int N, int SPC, int row_bytes, int SU, int sub) { return (long long)amajor_smem_bytes(N, SPC, row_bytes, SU, sub); }
 
 // amp: 0 c128, 1 c64, 2 r64
 extern "C" int qkan_emu_block_forward(int amp, int mode, int min_g, int tan, const double* x, const double* W, long long B, int N,

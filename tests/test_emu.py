@@ -58,15 +58,7 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
         x[2, :4] = [np.sqrt(0.5), -np.sqrt(0.5), 1e-300, -1.0]      # the quarter-turn boundary, a tiny and a unit input
     W = rng.uniform(-1, 1, (D + 1, N * K))
     spec = o.circuit_spec(N, K, D)
-    tan_ok = 1 <= D <= 16            # scaled-rotation form of the degree-specialised kernels (use_tan_form)
     cases = [(0, 0, 0, 1e-14), (0, 1, 0, 1e-14), (1, 0, 0, 1e-5), (2, 0, 0, 1e-14)]
-    if tan_ok:
-        cases += [(0, 0, 1, 1e-14), (1, 0, 1, 1e-5), (2, 0, 1, 1e-14)]
-        lay6 = (ctypes.c_int * 6)()
-        eff = ctypes.c_double()
-        emu.qkan_emu_block_layout(N, K, D, min_g, lay6, ctypes.byref(eff))
-        if lay6[0] == 1:             # U = 1 layouts: the window kernel's tables and per-row-step windows
-            cases += [(0, 0, 2, 1e-14), (1, 0, 2, 1e-5)]
     for amp, mode, tan, tol in cases:
         out = np.zeros((B, K))
         amps = np.zeros((B, K, 2))
@@ -76,6 +68,34 @@ def test_emulated_block_engine_matches_oracle(emu, N, K, D, min_g):
         assert np.abs(out - ref).max() <= tol
         assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
         assert np.abs(amps[..., 1]).max() == 0.0
+
+
+@pytest.mark.parametrize("min_g,max_gk", [(0, 5), (3, 5), (5, 5), (0, 0), (2, 1)])
+@pytest.mark.parametrize("N,K,D", [s for s in BLOCK_SHAPES if 1 <= s[2] <= 16] + [(6, 6, 7), (9, 2, 12), (64, 5, 16)])
+def test_emulated_amajor_kernels_match_oracle(emu, N, K, D, min_g, max_gk):
+    """qkan_amajor.cuh (layout planner, a-major tables, one CHEB evolution per (a, b) + SELECT per degree copy,
+    xor-butterfly read-out; main and window tables) run lane by lane."""
+    import ctypes
+    f = emu.qkan_emu_amajor_forward
+    f.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    rng = np.random.default_rng(N * 31 + K * 7 + D + min_g + 3 * max_gk)
+    B = 3
+    x = rng.uniform(-1.2, 1.2, (B, N))
+    x[1] = 0.0
+    if N >= 4:
+        x[2, :4] = [np.sqrt(0.5), -np.sqrt(0.5), 1e-300, -1.0]      # the quarter-turn boundary, a tiny and a unit input
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    spec = o.circuit_spec(N, K, D)
+    ref = o.forward_closed_form(x, W, N, K, D, "compat")
+    for amp, tol in ((0, 1e-14), (1, 1e-5), (2, 1e-14)):
+        for window in (0, 1):
+            out = np.zeros((B, K))
+            amps = np.zeros((B, K, 2))
+            rc = f(amp, min_g, max_gk, window, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data)
+            assert rc == 0
+            assert np.abs(out - ref).max() <= tol
+            assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
+            assert np.abs(amps[..., 1]).max() == 0.0
 
 
 def test_row_strides_are_bank_conflict_free(emu):

@@ -124,9 +124,10 @@ def test_out_of_range_inputs_clip_and_warn(Q, capsys):
 
 
 # ------------------------------------------------------------------- seeded oracle parity
-SHAPES = [(4, 4, 3), (4, 8, 2), (8, 4, 2), (3, 2, 4), (8, 8, 5), (5, 3, 1), (16, 16, 8), (8, 8, 1),
-          (8, 8, 2), (8, 8, 3), (8, 8, 4), (8, 8, 8), (8, 8, 16), (4, 4, 10), (4, 4, 20), (1, 1, 0),
-          (2, 2, 1), (1, 5, 2), (7, 1, 3), (33, 3, 2), (100, 10, 5), (4, 4, 31)]
+SHAPES = [(4, 4, 3), (4, 8, 2), (8, 4, 2), (3, 2, 4), (5, 3, 1), (16, 16, 8)] + \
+         [(8, 8, D) for D in range(1, 17)] + \
+         [(4, 4, 10), (4, 4, 20), (1, 1, 0), (2, 2, 1), (1, 5, 2), (7, 1, 3), (33, 3, 2), (100, 10, 5), (4, 4, 31),
+          (6, 5, 7), (12, 3, 9), (3, 11, 13)]          # every degree of the BASELINE configs[4] sweep is its own kernel
 
 
 @pytest.mark.parametrize("N,K,D", SHAPES)
@@ -274,8 +275,11 @@ def test_c_abi_direct(Q):
     info = b.KernelInfo()
     assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
     assert info.qubits == 8 and info.flops_survey == 21504 and info.grid > 0
-    assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 1 and info.flops_exec == 64 * (16 * 3 + 4)
-    assert info.fp_inst_exec == 64 * (8 * 3 + 4)
+    # per (a, b): one evolution through CHEB (2 full passes of 8 FMA + the pruned pass, 4 MUL + 4 FMA), then SELECT on
+    # each of the D + 1 degree copies (4 FMA)
+    assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 1 and info.degree_factored == 1
+    assert info.flops_exec == 16 * (16 * 2 + 12 + 8 * 4) and info.fp_inst_exec == 16 * (8 * 3 + 4 * 4)
+    assert info.flops_per_block_basis == 64 * (16 * 3 + 4)
     lib.qkan_layer_destroy(h)
     assert b.measure_fma_peak(0, True) > 5.0
 
@@ -329,8 +333,10 @@ def test_special_input_values(Q, N, K, D):
         assert_close(y, ref, dtype)
 
 
-@pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:128:4:4"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"}, {"QKAN_BLOCK_TUNE": "1:128:5:2"},
-                                 {"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"},
+@pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "1:256:3:1"}, {"QKAN_BLOCK_TUNE": "1:256:4:2"},
+                                 {"QKAN_BLOCK_TUNE": "1:256:3:2"}, {"QKAN_BLOCK_TUNE": "1:256:3:4"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"},
+                                 {"QKAN_BLOCK_TUNE": "1:128:8:1"}, {"QKAN_BLOCK_TUNE": "1:128:6:2"},
+                                 {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"}, {"QKAN_BLOCK_FORCE_WINDOW": "1"},
                                  {"QKAN_BLOCK_STRIDED": "1"}, {"QKAN_BLOCK_STRIDED": "0"}, {"QKAN_BLOCK_SUB": "1"},
                                  {"QKAN_BLOCK_SUB": "2"}, {"QKAN_BLOCK_NO_WINDOW": "1"}, {"QKAN_HOST_PATH": "staged"}])
 def test_tuning_variants_agree(Q, env, monkeypatch):
@@ -354,6 +360,21 @@ def test_tuning_variants_agree(Q, env, monkeypatch):
         op = torch.empty((B, K), dtype=torch.float64).pin_memory()
         layer.forward(xp.numpy(), W, out=op.numpy(), check_range=False)          # pinned: zero-copy (or staged by env)
         assert_close(op.numpy(), ref)
+
+
+@pytest.mark.parametrize("D", [0, 1, 3, 4, 16, 17])
+def test_any_width_creates_and_runs(Q, D):
+    """Kernel selection and launch agree on the shared-memory need for every input width (the selection once admitted
+    layouts whose launch was rejected around N = 355..383): create + forward over a sweep of N."""
+    rng = np.random.default_rng(D)
+    for K in (1, 4, 8):
+        W0 = rng.uniform(-1, 1, (D + 1, 820 * K))
+        x0 = rng.uniform(-1, 1, (5, 820))
+        for N in list(range(300, 420, 3)) + list(range(420, 820, 37)):
+            W = np.ascontiguousarray(W0[:, :N * K])
+            x = np.ascontiguousarray(x0[:, :N])
+            y = Q.QKANLayer(N, K, D).forward(x, W)
+            assert_close(y, o.forward_closed_form(x, W, N, K, D))
 
 
 @pytest.mark.parametrize("N,K,D,B", [(4, 4, 3, 1_000_000),        # BASELINE configs[1]

@@ -19,7 +19,7 @@ CONFIGS = {"c2": (4, 4, 3, 1_000_000), "c5d1": (8, 8, 1, 1_000_000), "c5d2": (8,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c5d1,c5d4,c5d16,c3")
-    ap.add_argument("--variants", default="0:0:0:0,1:256:4:1,1:128:8:1,1:256:3:2,1:128:6:2,2:256:3:1,4:256:2:1,4:128:4:1",
+    ap.add_argument("--variants", default="0:0:0:0,1:256:4:1,1:256:3:1,1:256:4:2,1:256:3:2,1:256:3:4,1:256:2:4,1:128:8:1,1:128:6:2",
                     help="QKAN_BLOCK_TUNE values U:NT:MINB:SU (0 = planner default); only built combinations resolve")
     ap.add_argument("--dtype", default="complex128")
     ap.add_argument("--prep", default="analytic")
@@ -67,6 +67,7 @@ def main():
                               "cta_per_sm": round(info["grid"] / 148, 2), "smem": info["smem_bytes"], "ms": round(ms, 4),
                               "samples_per_s": round(B / (ms * 1e-3)), "tflops_exec": round(tf, 2),
                               "frac": round(tf / peak, 3),
+                              "frac_per_block_basis": round(info["flops_per_block_basis"] * B / (ms * 1e-3) / 1e12 / peak, 3),
                               "pipe_util": round(info["fp_inst_exec"] * B / (ms * 1e-3) / (peak * 1e12 / 2), 3),
                               "frac_survey": round(info["flops_survey"] * B / (ms * 1e-3) / 1e12 / peak, 3), "bitwise_same": same}))
     os.environ.pop("QKAN_VARIANT", None)

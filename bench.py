@@ -2,15 +2,19 @@
 """bench.py - QKANLayer.forward samples/s on B200 (BASELINE.json metric) + roofline + CPU baseline.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--N 4 --K 4 --D 3 --batch 1000000 --dtype complex128 --prep analytic]
+                    [--N 4 --K 4 --D 3 --batch 1000000 --dtype complex128 --prep analytic] [--no-sweep]
 
 A "step" is one batched forward over `--batch` samples PER GPU (weak scaling; default = BASELINE
 configs[1]: N4 K4 D3, 1M samples, complex128).  `value` = samples of all ranks / max-over-ranks
-device time, inputs resident in HBM; for N > 1 the step includes the NCCL all-gather of the
-outputs (chunked, overlapped with compute).  `e2e` = the same metric through the public Python
-API with pinned HOST buffers (H2D + kernel + D2H inside the timed region).
-`--impl reference` times the CPU port of the reference's own algorithm (oracle/, one QKANLayer-
-style dense-NumPy forward per sample) on all host cores, rank 0 only.
+device time with inputs resident in HBM and the outputs left sharded: the samples are independent, so
+the path has NO data-path collective.  The north-star's "final gather" is timed separately in the same
+line: `with_output_gather` (NCCL all-gather, chunked and overlapped) and `with_fused_peer_gather` (the
+kernel stores every result to every rank: NVLS multicast / NVLink peer stores).
+`c5_sweep` = BASELINE configs[4]: N8 K8, 10 M samples IN TOTAL split over the ranks (strong scaling),
+D = 1 .. 16, each with sharded / NCCL-gather / fused-gather samples/s and roofline fractions.
+`e2e` = the same metric through the public Python API with pinned HOST buffers (H2D + kernel + D2H
+inside the timed region).  `--impl reference` times the CPU port of the reference's own algorithm
+(oracle/, one QKANLayer-style dense-NumPy forward per sample) on all host cores, rank 0 only.
 """
 import argparse
 import json
@@ -45,7 +49,39 @@ def parse():
     ap.add_argument("--cpu-samples", type=int, default=0, help="CPU baseline samples per worker (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the BASELINE configs[4] degree sweep (c5_sweep)")
+    ap.add_argument("--sweep-total", type=int, default=10_000_000, help="samples of the degree sweep, all ranks together")
+    ap.add_argument("--sweep-steps", type=int, default=5)
+    ap.add_argument("--sweep-degrees", default="1-16")
     return ap.parse_args()
+
+
+def csrc_sha():
+    """Hash of the kernel sources: ncu captures under profiles/ are only quoted for the code they were taken from."""
+    import hashlib
+    d = os.path.join(ROOT, "qkan_implementation_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    capture, written to profiles/r02_traffic.json by tools/ncu_traffic.py).  None when there is no capture of this
+    workload taken from the current kernel sources."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:      # noqa: BLE001
+        return None, "no profiles/r02_traffic.json"
+    e = tab.get(key)
+    if not e:
+        return None, f"no ncu capture of {key}"
+    if e.get("csrc_sha") != csrc_sha():
+        return None, f"capture {e.get('file')} is from other kernel sources ({e.get('csrc_sha')})"
+    return e["dram_bytes_read"] + e["dram_bytes_write"], f"profiles/{e.get('file')} (ncu --set full, per launch: read {e['dram_bytes_read']:.4g} B, write {e['dram_bytes_write']:.4g} B)"
 
 
 def workload_name(a):
@@ -205,6 +241,90 @@ def bind_to_gpu_numa_node(local: int):
     return None
 
 
+def run_c5_sweep(a, torch, dist, dev, world, rank, local, flush, timed):
+    """BASELINE configs[4]: QKANLayer N8 K8, D = 1 .. 16, `--sweep-total` samples IN TOTAL, rank r takes the contiguous
+    slice shard_bounds(total, world, r).  Per degree: the sharded step (`value`-style: no collective), the step with
+    an NCCL all-gather of the outputs, and the step whose kernel delivers every result to every rank (NVLS multicast).
+    Returns (rank 0) {"D": {...}}; times are max over ranks."""
+    from qkan_implementation_b200 import QKANLayer, _binding
+    from qkan_implementation_b200.distributed import shard_bounds
+    N = K = 8
+    total = a.sweep_total
+    lo, hi = shard_bounds(total, world, rank)
+    Bl = hi - lo
+    lo_d, hi_d = (int(v) for v in a.sweep_degrees.split("-")) if "-" in a.sweep_degrees else (int(a.sweep_degrees),) * 2
+    gx = torch.Generator().manual_seed(1000 + rank)
+    xd = (torch.rand((Bl, N), dtype=torch.float64, generator=gx) * 2 - 1).to(dev)
+    peak = _binding.measure_fma_peak(local, a.dtype != "complex64") if rank == 0 else 0.0
+    link = 770e9          # NVLink ingress per GPU measured on this pool (round 1): every rank must receive (world-1)/world of the result
+    out = {"workload": f"QKANLayer N=8 K=8 max_degree=1..16, {total} synthetic uniform(-1,1) inputs in total over {world} GPU(s), {a.dtype}",
+           "scaling": "strong", "samples_total": total, "samples_per_rank": Bl, "steps": a.sweep_steps, "fp_peak_tflops": peak,
+           "ingress_bound_ms": ((world - 1) / world * total * K * 8 / link * 1e3) if world > 1 else None, "degrees": {}}
+    full_buf = torch.empty((total, K), dtype=torch.float64, device=dev) if world > 1 else None
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    sizes_equal = total % world == 0
+    for D in range(lo_d, hi_d + 1):
+        W = torch.rand((D + 1, N * K), dtype=torch.float64, generator=torch.Generator().manual_seed(1)) * 2 - 1
+        layer = QKANLayer(N, K, D, dtype=a.dtype, device=local)
+        Wl = list(W.numpy())
+        layer._set_weights(Wl)
+        y = [None]
+
+        def step():
+            y[0] = layer._engine.forward_device(xd, False)[0]
+            return 1
+        t_ms, _, _, _ = timed(step, a.sweep_steps, 3)
+        info = layer.kernel_info()
+        rec = {"sharded": {"samples_per_s": total * a.sweep_steps / (t_ms * 1e-3), "ms_per_step": t_ms / a.sweep_steps}}
+        if world > 1 and sizes_equal:
+            nchunk = 4
+            cb = [(i * Bl // nchunk, (i + 1) * Bl // nchunk) for i in range(nchunk)]
+            parts = [torch.empty((world * (h - l), K), dtype=torch.float64, device=dev) for l, h in cb]
+
+            def step_gather():
+                cur = torch.cuda.current_stream(dev)
+                for c, (l, h) in enumerate(cb):
+                    yc = layer._engine.forward_device(xd[l:h], False)[0]
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    comm.wait_event(ev)
+                    with torch.cuda.stream(comm):
+                        dist.all_gather_into_tensor(parts[c], yc)
+                        yc.record_stream(comm)
+                cur.wait_stream(comm)
+                return nchunk
+            g_ms, _, _, _ = timed(step_gather, a.sweep_steps, 2)
+            rec["nccl_gather"] = {"samples_per_s": total * a.sweep_steps / (g_ms * 1e-3), "ms_per_step": g_ms / a.sweep_steps}
+            try:
+                from qkan_implementation_b200 import FusedGatherQKANLayer
+                fused = FusedGatherQKANLayer(layer, multicast=True)
+                fy = [None]
+
+                def step_fused():
+                    fy[0] = fused.forward(xd, Wl, total)
+                    return 1
+                f_ms, _, _, _ = timed(step_fused, a.sweep_steps, 2)
+                ref_list = [torch.empty_like(y[0]) for _ in range(world)]
+                dist.all_gather(ref_list, y[0])
+                same = bool(torch.equal(fy[0], torch.cat(ref_list, dim=0)))
+                rec["fused_gather"] = {"samples_per_s": total * a.sweep_steps / (f_ms * 1e-3), "ms_per_step": f_ms / a.sweep_steps,
+                                       "path": fused.last_path, "bitwise_equal_to_sharded": same,
+                                       "ingress_bound_frac": out["ingress_bound_ms"] / (f_ms / a.sweep_steps)}
+                del fused
+            except Exception as e:      # noqa: BLE001  (report, do not hide)
+                rec["fused_gather"] = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            sps = rec["sharded"]["samples_per_s"]
+            rec["sharded"]["frac"] = info["flops_exec"] * sps / 1e12 / (peak * world)
+            rec["sharded"]["frac_per_block_basis"] = info["flops_per_block_basis"] * sps / 1e12 / (peak * world)
+            rec["sharded"]["fp_pipe_utilisation"] = info["fp_inst_exec"] * sps / (peak * world * 1e12 / 2.0)
+            rec["flops_per_sample_executed"] = info["flops_exec"]
+            rec["kernel"] = {k: info[k] for k in ("samples_per_lane", "lanes_per_sample", "threads_per_cta", "min_ctas_per_sm", "direct_rows", "grid")}
+            out["degrees"][str(D)] = rec
+        del layer
+    return out if rank == 0 else None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -323,6 +443,11 @@ def run_ours(a):
                              "barrier; no NCCL collective in the step")
     do_gather = False
 
+    # ---- BASELINE configs[4]: degree sweep at N8 K8, 10 M samples in total, sharded over the ranks (strong scaling)
+    sweep = None
+    if not a.no_sweep and a.mode == "compat" and a.prep == "analytic":
+        sweep = run_c5_sweep(a, torch, dist, dev, world, rank, local, flush, timed)
+
     # ---- end-to-end through the public API with pinned host buffers
     e2e = None
     if not a.no_e2e:
@@ -332,12 +457,12 @@ def run_ours(a):
         oh = torch.empty((B, a.K), dtype=torch.float64).pin_memory()
         xn, on = xh.numpy(), oh.numpy()
         for _ in range(3):
-            layer.forward(xn, Wl, out=on, check_range=False)
+            layer.forward(xn, Wl, out=on)
         barrier()
         n_e2e = max(3, min(a.steps, 10))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            layer.forward(xn, Wl, out=on, check_range=False)
+            layer.forward(xn, Wl, out=on)                      # default flags: includes the reference's range check of x
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         te = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -345,8 +470,9 @@ def run_ours(a):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / float(te.item()), "unit": "samples/s", "h2d_bytes_per_step": B * a.N * 8,
                "d2h_bytes_per_step": B * a.K * 8, "steps": n_e2e, "cpus_bound_to_gpu_socket": numa,
-               "how": "QKANLayer.forward(numpy view of pinned host x, out=pinned host y), wall clock over the calls incl. the "
-                      "final sync, per rank, max over ranks.  Pinned buffers: the kernel itself streams x from host memory "
+               "host_path": os.environ.get("QKAN_HOST_PATH", "auto"),
+               "how": "QKANLayer.forward(numpy view of pinned host x, out=pinned host y) with default arguments (the range check of x "
+                      "included), wall clock over the calls incl. the final sync, per rank, max over ranks.  Pinned buffers: the kernel itself streams x from host memory "
                       "(TMA bulk loads over PCIe) and stores the results into the host buffer - no staging copies; pageable "
                       "buffers: chunked H2D / kernel / D2H on 3 streams (QKAN_HOST_PATH=staged forces that path)"}
         assert np.array_equal(on, outs[0].cpu().numpy()), "host path and device path disagree"
@@ -379,15 +505,16 @@ def run_ours(a):
         # the measured FMA peak is 2 flops per lane-instruction
         pipe_util = info["fp_inst_exec"] * B / (k_ms * 1e-3) / (peak * 1e12 / 2.0)
         io = (8 * a.N + 8 * a.K) * B
-        # DRAM bytes per launch of the dominant kernel from the ncu --set full capture of this workload
-        # (profiles/r01d_ncu_c2.txt: dram__bytes_read 32.03 MB + dram__bytes_write 0.20 MB; the 32 MB of outputs
-        # stay in the 126 MB L2).  Only known for the default workload.
-        traffic = None
-        if (a.N, a.K, a.D, a.batch, a.dtype, a.prep, a.mode) == (4, 4, 3, 1_000_000, "complex128", "analytic", "compat"):
-            traffic = 32.03e6 + 0.20e6
+        # DRAM bytes per launch of the dominant kernel: from the committed ncu capture of this workload, if it was taken
+        # from the kernel sources that are running (profiles/r02_traffic.json; tools/ncu_traffic.py)
+        tkey = f"N{a.N}_K{a.K}_D{a.D}_B{a.batch}_{a.dtype}_{a.prep}_{a.mode}"
+        traffic, traffic_src = measured_traffic(tkey)
+        ach_pb = info["flops_per_block_basis"] * B / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "fp64" if fp64 else "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r01d_ncu_c2.txt (ncu --set full, per launch)" if traffic else None,
-                    "kernel_ms": k_ms,
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel_ms": k_ms,
+                    "achieved_per_block_basis": ach_pb, "frac_per_block_basis": ach_pb / peak,
+                    "flops_per_sample_per_block_basis": info["flops_per_block_basis"],
+                    "degree_factored": info.get("degree_factored"), "cheb_evaluations_per_sample": info.get("cheb_elements"),
                     "fp_pipe_utilisation": pipe_util,
                     "flops_per_sample_executed": info["flops_exec"], "fp_instructions_per_sample": info["fp_inst_exec"],
                     "flops_per_sample_survey": info["flops_survey"],
@@ -396,12 +523,16 @@ def run_ours(a):
                     "peak_source": "qkan_measure_fma_peak: independent %s chains on all SMs, measured in this run" % ("DFMA" if fp64 else "FFMA"),
                     "hbm": {"algorithmic_bytes_per_sample": 8 * a.N + 8 * a.K, "achieved_gbs": io / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm,
                             "frac": io / (k_ms * 1e-3) / 1e9 / hbm, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-                    "note": "achieved = arithmetic the kernel really executes (DFMA=2, DMUL=DADD=1 flop; "
-                            + ("scaled-rotation kernel: a CHEB pass is one FMA per real output - Ry = gamma*M(t), gamma^D and the quarter "
-                               "turns deferred to the last pass - so nearly every issue slot is an FMA"
-                               if info.get("scaled_rotations") else
-                               "rotations are 6 flops in 4 instructions so 0.75 is the ceiling of frac at 100% pipe utilisation")
-                            + "); *_survey_flops credits SURVEY 8(d) "
+                    "note": "achieved / frac = arithmetic the kernel really executes (DFMA=2, DMUL=DADD=1 flop) over the measured "
+                            "DFMA peak. "
+                            + ("This round's kernels run the CHEB sequence once per input element - the D+1 degree copies of a "
+                               "block and the blocks that read the same input share it (circuit structure: CHEB does not act on deg, "
+                               "the multiplexor's angle table has N distinct entries) - and SELECT once per (a,b,d) block, so they "
+                               "execute 8DN + 4NK(D+1) FP instructions per sample where round 1 executed NK(D+1)(8D+4); "
+                               "*_per_block_basis credits the round-1 count for the same time (comparable with BENCH_r01), and is "
+                               "> 1 when the saved arithmetic exceeds what the pipe could have done. "
+                               if info.get("degree_factored") else "")
+                            + "*_survey_flops credits SURVEY 8(d) "
                             "F_alg = 6*S*P for the same time (the kernel prepares |+> in closed form, skips padded blocks and prunes the "
                             "last layer to the post-selected outputs, so it executes fewer flops than F_alg)"}
         # the literal Appendix-C simulation (prep="gates": every gate incl. the initial Hadamards is a pass over the
@@ -441,7 +572,7 @@ def run_ours(a):
                 "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": world * B, "mode": a.mode, "prep": a.prep,
                            "l2": "flushed between timed steps (256 MiB device write)",
                            "sharding": "contiguous batch slice per rank, weights replicated, no data-path collective", "kernel": info},
-                "clocks": clocks, "e2e": e2e, "with_output_gather": gather_line, "with_fused_peer_gather": fused_line, "gpu_launches": launches, "roofline": roofline, "gates_engine": gates, "cpu_baseline": cpu,
+                "clocks": clocks, "e2e": e2e, "with_output_gather": gather_line, "with_fused_peer_gather": fused_line, "c5_sweep": sweep, "gpu_launches": launches, "roofline": roofline, "gates_engine": gates, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:

@@ -115,9 +115,15 @@ typedef struct {
                                    mode, 1 <= D <= 16); 0: plain (cos, sin) rotations                         */
     int input_window;           /* > 0: window kernel (wide input rows) - rotation entries are built per row step
                                    from this many inputs instead of once per sample from all N                 */
-    int degree_factored;        /* 1: the D + 1 degree copies of an (a, b) block share ONE evolution through the CHEB
-                                   sequence (the state is (block) (x) |+>_deg until SELECT) and SELECT is then applied
-                                   per copy: 12 D + 4 FP instructions per (a, b) instead of (8 D + 4)(D + 1)       */
+    int degree_factored;        /* 1: a-major kernels - blocks that share a CHEB evolution share its arithmetic: the D + 1
+                                   degree copies of an (a, b) block (the state is (block) (x) |+>_deg until SELECT) and
+                                   the blocks that read the same input element x[(a + N b) / K] (repeated entries of
+                                   the multiplexor's angle table).  CHEB runs once per input element, SELECT per block:
+                                   8 D N + 4 N K (D+1) FP instructions per sample instead of N K (D+1)(8 D + 4)   */
+    int cheb_elements;          /* CHEB evaluations per sample: N (window kernel: the sum of the row steps' windows;
+                                   direct kernel: K)                                                            */
+    int direct_rows;            /* 1: direct kernel - every output row reads one input element (K a multiple of N): the
+                                   lane of the row evaluates it in registers, no shared memory / barriers / tiles  */
     double flops_survey;        /* 6 * 2^qubits * ((D+1) + m + 2l + n_a)                     */
     double flops_per_block_basis; /* round-1 accounting: every (a, b, d) block evolved on its own through the whole
                                    sequence, (16 D + 4) flops each in the scaled form - reported so that throughput can

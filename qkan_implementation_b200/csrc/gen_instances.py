@@ -96,13 +96,18 @@ def block_instances():
 # (SU, NT) -> [(MINB, is_default)].  SU = samples per lane at a time.  Non-default entries are tuning variants
 # (QKAN_BLOCK_TUNE=1:NT:MINB:SU), built for complex128 only.
 AMAJOR = {
-    (1, 256): [(4, 1), (3, 0)],
-    (2, 256): [(4, 0), (3, 1)],
-    (4, 256): [(3, 0), (2, 1)],
+    (2, 256): [(3, 1)],
+    (1, 256): [(4, 1)],      # fall-backs when two samples' rows do not fit (wide input rows)
     (1, 128): [(8, 1)],
-    (2, 128): [(6, 1)],
 }
-WINDOW_CTAS = ((256, 4, 1), (256, 3, 0))   # (NT, MINB, is_default) of the window kernels (wide input rows)
+# direct kernels (every output row reads one input element: K a multiple of N, K a power of two): (SU, NT) -> [(MINB, is_default)]
+# measured best on every BASELINE shape: four samples per lane, 256-thread CTAs, two CTAs per SM
+# (profiles/r02e_tune_direct.jsonl, r02d_tune_direct_all.jsonl)
+DIRECT = {
+    (4, 256): [(2, 1)],
+    (2, 256): [(3, 0)],      # tuning variant (complex128 only)
+}
+WINDOW_CTAS = ((256, 3, 1),)   # (NT, MINB, is_default) of the window kernels (wide input rows); MINB 4 measured slower on N784 K10 D5
 
 
 def amajor_instances():
@@ -110,6 +115,18 @@ def amajor_instances():
     for amp in ("c128", "c64", "r64"):
         for dt in range(1, DT_MAX + 1):
             for (SU, NT), variants in AMAJOR.items():
+                for (minb, dflt) in variants:
+                    if not dflt and amp != "c128":
+                        continue
+                    out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
+    return out
+
+
+def direct_instances():
+    out = []   # (group, amp, SU, NT, MINB, DT, is_default)
+    for amp in ("c128", "c64", "r64"):
+        for dt in range(1, DT_MAX + 1):
+            for (SU, NT), variants in DIRECT.items():
                 for (minb, dflt) in variants:
                     if not dflt and amp != "c128":
                         continue
@@ -148,6 +165,9 @@ def main():
     agroups = {}
     for it in amajor_instances():
         agroups.setdefault(it[0], []).append(it)
+    dgroups = {}
+    for it in direct_instances():
+        dgroups.setdefault(it[0], []).append(it)
     wgroups = {}
     for it in window_instances():
         wgroups.setdefault(it[0], []).append(it)
@@ -191,6 +211,9 @@ def main():
         for (_, amp, SU, NT, MINB, DT, dflt) in items:
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_amajor_info<{A}, {R}, {SU}, {NT}, {MINB}, {DT}>({dflt}));\n")
+        for (_, amp, SU, NT, MINB, DT, dflt) in dgroups.get(g, []):
+            A, R, _sz = AMPS[amp]
+            fh.write(f"    reg.push_back(make_direct_info<{A}, {R}, {SU}, {NT}, {MINB}, {DT}>({dflt}));\n")
         for (_, amp, NT, MINB, DT, dflt) in wgroups.get(g, []):
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_amajor_window_info<{A}, {R}, {NT}, {MINB}, {DT}>({dflt}));\n")

@@ -1,25 +1,42 @@
 // qkan_amajor.cuh - the default forward kernels of the block engine (compat mode, 1 <= D <= 16).
 //
-// Same circuit, same per-block arithmetic as qkan_block.cuh (scaled rotations, evolve_blocks_tan), but the
-// lane's blocks are walked "a-major": the D + 1 blocks (a, b, d = 0 .. D) of one (a, b) are consecutive.
-// Their CHEB rotation is the same multiplexor entry - x[(a + N b) / K] does not depend on d
-// (ChebyshevStep.py:64, MulStep.py:59) - so the (t, alpha, beta) triple is fetched ONCE per (a, b) and kept
-// in registers while the D + 1 blocks are evolved; per block the kernel only streams the SELECT rotation
-// (cos, sin)(theta_w / 2) through one pointer with immediate offsets.  Against the slot-major walk of
-// round 1 (three LDS.64 + one table-offset load + pointer bumps per block) this removes about
-// 3 of 4 non-arithmetic instructions of a shallow sequence (ncu: profiles/r02_ncu_*.txt).
+// Same circuit as qkan_block.cuh, simulated block by block in the scaled-rotation form, but
+// using two more facts about the circuit's STRUCTURE (nothing that depends on the input values):
 //
-// Mapping: one sample = G = G_k * G_r lanes of one warp.  Lane (k, r) owns output rows b = bi G_k + k and,
-// in row b, the summed indices a = pi G_r + r, pi = 0 .. passes - 1 (passes = ceil(N / G_r)); all D + 1
-// degree blocks of (a, b) are evolved by that lane.  UNPREPARE + SUM + post-selection on deg = a = 0 is the
-// lane's running sum, finished across the G_r lanes of the row by an xor butterfly.
+//  (1) CHEB acts on f_x only, and PREPARE leaves every index register in a product state.  Until SELECT the
+//      statevector is therefore  sum_(a,b) |a,b> (x) (block state of (a,b)) (x) |+>_deg : the D + 1 degree copies
+//      of an (a, b) block hold the SAME four amplitudes, so they are evolved through the CHEB sequence once, not
+//      D + 1 times.  (With the rotation entry in registers the D + 1 evolutions are literally common
+//      subexpressions - ptxas merged them in a kernel that spelled out every block - so the code says it.)
+//  (2) The CHEB multiplexor UCRy(theta_x) is controlled by (a, b) but its angle table has only N distinct entries:
+//      theta_x[a, b] = theta(x[(a + N b) / K])  (np.repeat dilation, ChebyshevStep.py:64, against the column-major
+//      SUM reshape, QKANLayer.py:132).  Blocks that share the entry share the evolution, so the CHEB sequence is
+//      run once per INPUT ELEMENT: the pre-pass over a tile's inputs produces, per element, the two f_x = 0 block
+//      amplitudes after CHEB, (lo0, lo2) = (f_w = 0, f_w = 1): 8 (D - 1) FMA + 4 MUL + 4 FMA per element.
+//
+// SELECT (MUL) is controlled by (a, b, deg): every one of the N K (D + 1) blocks gets its own rotation
+// (cos, sin)(theta_w / 2), applied to its copy of (lo0, lo2) and fused with the read-out sum: 4 FMA per block.
+// No weight is pre-summed and nothing state dependent is skipped (the f_w = 1 half and the imaginary parts are
+// zero at run time and are evolved like any other amplitude; the prepared block state is a kernel parameter).
+// Per sample: 8 D N + 4 N K (D + 1) FP instructions, against N K (D + 1)(8 D + 4) when every block is evolved on
+// its own (round 1; qkan_kernel_info.flops_per_block_basis keeps that count for comparison).
+//
+// Mapping: one sample = G = G_k * G_r lanes of one warp.  Lane (k, r) owns output rows b = bi G_k + k and, in
+// row b, the summed indices a = pi G_r + r, pi = 0 .. passes - 1 (passes = ceil(N / G_r)); it applies SELECT to
+// all D + 1 degree copies of (a, b).  UNPREPARE + SUM + post-selection on deg = a = 0 is the lane's running sum,
+// finished across the G_r lanes of the row by an xor butterfly.  A lane re-reads (lo0, lo2) from shared memory only
+// when the input element changes from one a to the next (never, for K a multiple of N).
 //
 // Tables (built once per set_weights by qkan_prepare_amajor_tables_kernel):
 //     step = ((bi * passes + pi) << g_log2) + g,   g = (k << g_r_log2) | r
-//     wtab[step * (D + 1) + d] = (cos, sin)(theta_w / 2) of block (a, b, d): W[d][a + N b] (column-major SUM
-//                                reshape, QKANLayer.py:132; MulStep.py:69); a lane's D + 1 entries are contiguous
-//     xotab[step]              = byte offset of the (t, alpha, beta) triple of x[(a + N b) / K] in the sample's
-//                                cs row (window kernel: relative to the row step's input window)
+//     wtab[(((bi * passes + pi) * (D + 1) + d) << g_log2) + g]
+//                              = (cos, sin)(theta_w / 2) of block (a, b, d): W[d][a + N b] (MulStep.py:69); the lane is
+//                                the fastest index, so one warp load reads one contiguous run of G entries (one 128-byte
+//                                line for G <= 8 in FP64: the L1 pipe takes about two cycles per line a load touches, and
+//                                a lane-major table - D + 1 entries of a lane contiguous - made every load touch G lines,
+//                                which bound the deep sequences, profiles/r02c_tune_*.jsonl)
+//     xotab[step]              = byte offset of lo0 of x[(a + N b) / K] in the sample's cs row (window kernel:
+//                                relative to the row step's input window); lo2 sits `plane` bytes further
 // Padding steps (a >= N or b >= K, and one extra pass at the end for the prefetch) rotate by theta = pi and read
 // the row's dummy entry (x = 0): they add exactly 0.
 #pragma once
@@ -50,7 +67,7 @@ inline BlockLayout plan_amajor_layout(int N, int K, int min_g_log2 = 0, int max_
     return best;
 }
 
-// table entries of one (bi, pi, lane) step: D + 1 SELECT rotations and the offset of the CHEB triple
+// table entries of one (bi, pi, lane) step: D + 1 SELECT rotations and the offset of the element's lo0
 template <typename R>
 QK_HD void fill_amajor_step(long long step, const double* W, int N, int K, int D, int passes, int brows, int g_r_log2,
                             int g_k_log2, CS<R>* wtab, int* xotab, int x_entry_bytes, int window) {
@@ -80,13 +97,34 @@ QK_HD void fill_amajor_step(long long step, const double* W, int N, int K, int D
             q.c = w;
             q.s = qk_sqrt((R(1) - w) * (R(1) + w));
         }
-        wtab[step * (D + 1) + d] = q;
+        wtab[((((step >> g_log2) * (D + 1)) + d) << g_log2) + g] = q;
     }
 }
 
 // steps of the tables: every (row step, pass, lane) plus one pass of padding (the kernels prefetch one pass ahead)
 inline long long amajor_steps(const BlockLayout& lay) {
     return ((long long)lay.brows * lay.passes + 1) << (lay.g_r_log2 + lay.g_k_log2);
+}
+
+// A sample's cs row: two planes of n1 = N + 1 amplitudes (lo0[0 .. N], lo2[0 .. N]; index N = the dummy, x = 0),
+// `amp_bytes` each.  Returns the row stride in amplitudes (>= 2 n1; every amplitude stays naturally aligned).  One shared-memory
+// phase serves 128 bytes = P lanes; with G < P lanes per sample a phase spans P / G consecutive sample rows whose
+// lanes read G consecutive amplitudes of a plane, so the stride is chosen to spread them over the P slots.
+inline int amajor_row_amps(int n1, int G, int amp_bytes) {
+    const int P = 128 / amp_bytes;
+    const int need = 2 * n1;
+    if (G >= P || n1 > 2 * P) return need;
+    int best = need, best_worst = 1 << 30;
+    for (int rs = need; rs < need + P; ++rs) {
+        int cnt[32] = {0};
+        int worst = 0;
+        for (int lane = 0; lane < P; ++lane) {
+            const int w = ((lane / G) * rs + (lane % G) % n1) % P;
+            if (++cnt[w] > worst) worst = cnt[w];
+        }
+        if (worst < best_worst) { best_worst = worst; best = rs; }
+    }
+    return best;
 }
 
 // shared memory of the main kernel for a tile of `sub` sub-iterations (SPC samples each): two raw-x TMA buffers
@@ -99,39 +137,35 @@ inline size_t amajor_smem_bytes(int N, int SPC, int row_bytes, int SU, int sub) 
     const size_t cs = ((tile + (size_t)(SU - 1) * SPC) * (size_t)row_bytes + 15) & ~(size_t)15;
     return xs + cs + 16;
 }
+inline size_t amajor_window_smem_bytes(int SPC, int row_bytes, int sub) { return (size_t)SPC * sub * row_bytes; }
 constexpr size_t AMAJOR_SMEM_CAP = 200 * 1024;
 
-// The D + 1 blocks (a, b, d = 0 .. D) of SU samples: CHEB triples in registers, SELECT rotations streamed from `wp`.
-//
-// CHEB acts on f_x only and PREPARE leaves deg in the product state |+>^l, so until SELECT the statevector is
-// (block state of (a, b)) (x) |+>_deg: the D + 1 blocks of one (a, b) hold the SAME four amplitudes.  With the triple
-// in registers their D + 1 evolutions are literally common subexpressions (ptxas merges them whether or not the source
-// spells it out - an earlier version that evolved every block separately compiled to this code), so the function says
-// it explicitly: the block state is evolved ONCE through the CHEB sequence (8 (D - 1) FMA + the pruned last pass,
-// 4 MUL + 4 FMA) and the SELECT rotation is then applied to each of the D + 1 copies with its own angle (4 FMA per
-// block, fused with the read-out sum).  Exact; no weight is pre-summed - every (a, b, d) amplitude gets its own SELECT
-// rotation.  Per (a, b): 12 D + 4 FP instructions / 24 D + 4 flops (complex amplitudes), against (8 D + 4)(D + 1)
-// when every block is evolved on its own (round 1).
-template <class A, typename R, int SU, int DT>
-QK_HD void amajor_blocks(const A (&init)[4], const TanEntry<R> (&e)[SU], const CS<R>* __restrict__ wp,
-                                              A (&acc)[SU]) {
-    A lo0[SU], lo2[SU];
+// CHEB on one input element: the block state `init` through D applications of Ry(theta_x), cos(theta_x / 2) = c,
+// in the scaled form (D - 1 full passes M(t), then the pruned pass alpha u + beta v with gamma^D and the quarter
+// turns); returns the f_x = 0 amplitudes of the two f_w halves.
+template <class A, typename R, int DT>
+QK_HD void cheb_element(const A (&init)[4], R c, A& lo0, A& lo2) {
+    const TanEntry<R> e = tan_entry<R>(c, DT);
+    A v[4];
     QK_UNROLL
-    for (int j = 0; j < SU; ++j) {
-        A v[4];
-        QK_UNROLL
-        for (int q = 0; q < 4; ++q) v[q] = init[q];
-        QK_UNROLL
-        for (int r = 0; r + 1 < DT; ++r) {
-            rot_tan(v[0], v[1], e[j].t);
-            rot_tan(v[2], v[3], e[j].t);
-        }
-        lo0[j] = lin2(v[0], v[1], e[j].al, e[j].be);
-        lo2[j] = lin2(v[2], v[3], e[j].al, e[j].be);
+    for (int q = 0; q < 4; ++q) v[q] = init[q];
+    QK_UNROLL
+    for (int r = 0; r + 1 < DT; ++r) {
+        rot_tan(v[0], v[1], e.t);
+        rot_tan(v[2], v[3], e.t);
     }
+    lo0 = lin2(v[0], v[1], e.al, e.be);
+    lo2 = lin2(v[2], v[3], e.al, e.be);
+}
+
+// SELECT on the D + 1 degree copies of SU samples' (a, b) block, fused with the read-out sum:
+// acc += cos(theta_w / 2) lo0 - sin(theta_w / 2) lo2   (the (f_x, f_w) = (0, 0) output of Ry(theta_w) on f_w)
+// wp -> the lane's entry of degree 0; consecutive degrees are G entries apart
+template <class A, typename R, int SU, int DT>
+QK_HD void select_blocks(const A (&lo0)[SU], const A (&lo2)[SU], const CS<R>* __restrict__ wp, int G, A (&acc)[SU]) {
     QK_UNROLL
     for (int d = 0; d <= DT; ++d) {
-        const CS<R> q = wp[d];
+        const CS<R> q = wp[(size_t)d * G];
         QK_UNROLL
         for (int j = 0; j < SU; ++j) {
             fma_amp(acc[j], q.c, lo0[j]);
@@ -140,16 +174,27 @@ QK_HD void amajor_blocks(const A (&init)[4], const TanEntry<R> (&e)[SU], const C
     }
 }
 
+// direct kernel applies: one row step, one lane per row, each row reads a single input element
+inline bool amajor_direct_ok(int N, int K, const BlockLayout& lay) {
+    return K % N == 0 && lay.g_r_log2 == 0 && lay.brows == 1 && lay.efficiency == 1.0;
+}
+
 #if defined(__CUDACC__)
+// result store.  plain: one local buffer, no amplitudes (a single uniform branch in the hot path)
 template <class A, typename R>
-__device__ __forceinline__ void amajor_store(const BlockParams& p, const A& acc, long long o, long long oa) {
-    store_result(p, o, (double)acc.re * p.out_scale);
-    if (p.amps) {
+__device__ __forceinline__ void amajor_store(const BlockParams& p, const A& acc, double* __restrict__ out_t, void* amps_t, int o) {
+    const double val = (double)acc.re * p.out_scale;
+    if (p.plain) {
+        out_t[o] = val;
+        return;
+    }
+    store_result(p, (long long)(out_t - p.outs[0]) + o, val);
+    if (amps_t) {
         Cplx<R> z;
         z.re = (R)((double)acc.re * p.amp_scale);
         if constexpr (A::is_complex) z.im = (R)((double)acc.im * p.amp_scale);
         else z.im = R(0);
-        reinterpret_cast<Cplx<R>*>(p.amps)[oa] = z;
+        reinterpret_cast<Cplx<R>*>(amps_t)[o] = z;
     }
 }
 
@@ -161,10 +206,10 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
     const int G = p.G, G_r = p.G_r, G_k = p.G_k;
     const int SPC = p.SPC;                                   // samples in flight per CTA
     const int tile = p.tile;                                 // samples per x tile
-    const int RB = p.row_bytes;                              // cs row stride: N triples + the dummy (+ padding)
-    constexpr size_t ENTB = sizeof(TanEntry<R>);
+    const int RB = p.row_bytes;                              // cs row stride
+    const int plane = p.plane_bytes;                         // lo2 plane offset inside a row
     constexpr int D1 = DT + 1;
-    // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs (rotation triples of the current tile, plus
+    // smem: xs[2] (TMA destinations: raw x rows, two tiles in flight) | cs ((lo0, lo2) of the current tile's inputs, plus
     // SU - 1 sub-iterations of slack rows: the idle slots of a ragged tile read past its last row) | mbar[2]
     const size_t xs_doubles = p.direct_x ? 0 : (((size_t)tile * p.N + 1) & ~(size_t)1);
     double* xs0 = reinterpret_cast<double*>(smem_raw);
@@ -183,37 +228,42 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
     const long long base = strided ? 0 : ((long long)blockIdx.x * p.s_tot / gridDim.x) * SPC;
     const long long bend_raw = strided ? p.B : (((long long)blockIdx.x + 1) * p.s_tot / gridDim.x) * SPC;
     const long long bend = bend_raw < p.B ? bend_raw : p.B;
-    const long long it_step = strided ? (long long)gridDim.x : 1;
-    const long long n_it = (bend - base + tile - 1) / tile;
+    const int it_step = strided ? (int)gridDim.x : 1;
+    const int n_it = (int)((bend - base + tile - 1) / tile);
     const CS<R>* __restrict__ wtab = reinterpret_cast<const CS<R>*>(p.cstab);
     const int* __restrict__ xotab = p.xotab;
 
+    A init[4];
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        init[q].re = (R)p.init[2 * q];
+        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
+    }
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         fence_barrier_init();
     }
-    for (int i = tid; i < tile + (SU - 1) * SPC; i += NT) {   // the dummy entries never change; slack rows are all-dummy
-        const TanEntry<R> dm = tan_entry<R>(R(0), DT);
-        if (i < tile) {
-            *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + p.N * ENTB) = dm;
-        } else {
-            for (int n = 0; n <= p.N; ++n) *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + n * ENTB) = dm;
+    {   // the dummy entries (x = 0) never change
+        A d0, d2;
+        cheb_element<A, R, DT>(init, R(0), d0, d2);
+        for (int i = tid; i < tile + (SU - 1) * SPC; i += NT) {
+            *reinterpret_cast<A*>(cs + (size_t)i * RB + p.N * sizeof(A)) = d0;
+            *reinterpret_cast<A*>(cs + (size_t)i * RB + plane + p.N * sizeof(A)) = d2;
         }
     }
     __syncthreads();
 
-    auto tile_bytes = [&](long long it) -> unsigned {
-        const long long s0 = base + it * tile;
-        const int ns = (int)((bend - s0 < tile) ? (bend - s0) : tile);
-        return (unsigned)ns * (unsigned)p.N * 8u;
+    auto tile_samples = [&](int i) -> int {
+        const long long left = bend - (base + (long long)i * tile);
+        return left < tile ? (int)left : tile;
     };
-    // stage the x rows of tile `it` into buffer b: one 1-D TMA bulk copy when the tile is 16-byte
+    // stage the x rows of a tile into buffer b: one 1-D TMA bulk copy when the tile is 16-byte
     // granular, plain coalesced loads otherwise (ragged tail, odd N)
-    auto issue_x = [&](long long it, int b) {
+    auto issue_x = [&](int i, int b) {
         if (p.direct_x) return;
-        const unsigned bytes = tile_bytes(it);
-        const double* src = p.x + (base + it * tile) * p.N;
+        const unsigned bytes = (unsigned)tile_samples(i) * (unsigned)p.N * 8u;
+        const double* src = p.x + (base + (long long)i * tile) * p.N;
         double* dst = xs0 + (size_t)b * xs_doubles;
         if (p.tma_ok && (bytes & 15u) == 0) {
             if (tid == 0) {
@@ -222,21 +272,15 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
                 tma_load_1d(dst, src, bytes, &mbar[b]);
             }
         } else {
-            for (int i = tid; i < (int)(bytes >> 3); i += NT) dst[i] = src[i];
+            for (int q = tid; q < (int)(bytes >> 3); q += NT) dst[q] = src[q];
         }
     };
 
-    A init[4];
-    QK_UNROLL
-    for (int q = 0; q < 4; ++q) {
-        init[q].re = (R)p.init[2 * q];
-        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
-    }
     const int x0 = xotab[g];                                  // first step's offset: resident for the whole launch
     const size_t wstep = (size_t)G * D1;                      // table entries between consecutive passes of a lane
 
     // two tiles in flight: tile i is consumed while tiles i+1 and (after its pre-pass) i+2 are loading
-    long long it = strided ? (long long)blockIdx.x : 0;
+    int it = strided ? (int)blockIdx.x : 0;
     unsigned phase0 = 0, phase1 = 0;
     int buf = 0;
     if (it < n_it) issue_x(it, 0);
@@ -246,76 +290,87 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
     // (NT / N, NT % N) per step, so the loop has no division
     const int pre_row0 = tid / p.N, pre_n0 = tid - pre_row0 * p.N;
     const int pre_dr = NT / p.N, pre_dn = NT - pre_dr * p.N;
+    char* const pre_dst0 = cs + (size_t)pre_row0 * RB + pre_n0 * (int)sizeof(A);
+    const int pre_step = pre_dr * RB + pre_dn * (int)sizeof(A);       // bytes per walk step without the row wrap
+    const int pre_wrap = RB - p.N * (int)sizeof(A);                   // extra bytes when n wraps into the next row
 
-    const size_t row_stride = (size_t)SPC * RB;                   // bytes between consecutive sub-iterations
-    const long long out_stride = (long long)SPC * p.K;
+    const int row_stride = SPC * RB;                          // bytes between consecutive sub-iterations
+    const int out_stride = SPC * p.K;
+    const char* const csrow0 = cs + (size_t)slot * RB;
 
     for (; it < n_it; it += it_step, buf ^= 1) {
-        if (!p.direct_x && p.tma_ok && (tile_bytes(it) & 15u) == 0) {
+        const int nsamp = tile_samples(it);
+        if (!p.direct_x && p.tma_ok && ((nsamp * p.N) & 1) == 0) {
             if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
             else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
         }
-        const long long s0 = base + it * tile;
+        const long long s0 = base + (long long)it * tile;
         const double* xs = p.direct_x ? p.x + s0 * p.N : xs0 + (size_t)buf * xs_doubles;
-        const int nsamp = (int)((bend - s0 < tile) ? (bend - s0) : tile);
 
         // pre-pass over the raw inputs of the tile: range count (the reference prints a warning,
-        // ChebyshevStep.py:46-49), clip (:52) and the scaled-rotation triple of cos(theta/2) = x - no arccos
+        // ChebyshevStep.py:46-49), clip (:52) and the CHEB sequence of the element: cos(theta/2) = x, no arccos
         unsigned bad = 0;
         {
             const int n_in = nsamp * p.N;
-            int row = pre_row0, n = pre_n0;
+            int n = pre_n0;
+            char* dst = pre_dst0;
             for (int e = tid; e < n_in; e += NT) {
                 const double v = xs[e];
                 if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
-                *reinterpret_cast<TanEntry<R>*>(cs + (size_t)row * RB + n * ENTB) = tan_entry<R>(clip_unit<R>(v), DT);
+                A lo0, lo2;
+                cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0, lo2);
+                *reinterpret_cast<A*>(dst) = lo0;
+                *reinterpret_cast<A*>(dst + plane) = lo2;
                 n += pre_dn;
-                row += pre_dr;
-                if (n >= p.N) { n -= p.N; ++row; }
+                dst += pre_step;
+                if (n >= p.N) { n -= p.N; dst += pre_wrap; }
             }
         }
         if (bad) atomicAdd(p.oor, (unsigned long long)bad);
         __syncthreads();                                      // cs complete, xs[buf] free again
-        const long long nxt = it + 2 * it_step;
-        if (nxt < n_it) issue_x(nxt, buf);                    // overlaps with the compute of this and the next tile
+        if (it + 2 * it_step < n_it) issue_x(it + 2 * it_step, buf);   // overlaps with the compute of this and the next tile
 
         // SU samples per lane at a time (the lane's slots of SU consecutive sub-iterations): they share every
         // SELECT entry and the per-pass bookkeeping
-        const int nsub = (nsamp + SPC - 1) / SPC;
-        const char* csrow = cs + (size_t)slot * RB;
-        long long o = (p.row0 + s0 + slot) * p.K;
-        long long oa = (s0 + slot) * p.K;                     // amps are local: no row offset
-        int ls = slot;
-        for (int si = 0; si < nsub; si += SU, csrow += SU * row_stride, o += SU * out_stride, oa += SU * out_stride, ls += SU * SPC) {
-            bool valid[SU];
+        double* const out_t = p.outs[0] + (p.row0 + s0) * p.K;
+        void* const amps_t = p.amps ? (void*)(reinterpret_cast<Cplx<R>*>(p.amps) + s0 * p.K) : nullptr;
+        const char* csrow = csrow0;
+        int o = slot * p.K;
+        // whole sub-iterations (every lane of a sample group runs: the butterfly needs all of them)
+        const int ls_end = (nsamp + SPC - 1) & ~(SPC - 1);
+        for (int ls = slot; ls < ls_end; ls += SU * SPC, csrow += SU * row_stride, o += SU * out_stride) {
             const char* row[SU];
             QK_UNROLL
-            for (int j = 0; j < SU; ++j) {
-                valid[j] = ls + j * SPC < nsamp;
-                row[j] = csrow + j * row_stride;      // idle slots of a ragged tile evolve a stale / slack row; nothing is stored
-            }
-            const CS<R>* wp = wtab + (size_t)g * D1;
+            for (int j = 0; j < SU; ++j) row[j] = csrow + j * row_stride;      // idle slots of a ragged tile evolve a stale / slack row; nothing is stored
+            const CS<R>* wp = wtab + g;
             const int* xp = xotab + g;
-            int xo = x0;
-            A acc[SU];
+            int xo = x0, xprev = -1;
+            A acc[SU], lo0[SU], lo2[SU];
             auto run_row = [&]() {
                 QK_UNROLL
                 for (int j = 0; j < SU; ++j) set_amp(acc[j], 0.0);
                 for (int pi = 0; pi < p.passes; ++pi) {
-                    TanEntry<R> e[SU];
-                    QK_UNROLL
-                    for (int j = 0; j < SU; ++j) e[j] = *reinterpret_cast<const TanEntry<R>*>(row[j] + xo);
+                    if (xo != xprev) {                        // a new input element (predicated loads)
+                        QK_UNROLL
+                        for (int j = 0; j < SU; ++j) {
+                            lo0[j] = *reinterpret_cast<const A*>(row[j] + xo);
+                            lo2[j] = *reinterpret_cast<const A*>(row[j] + plane + xo);
+                        }
+                        xprev = xo;
+                    }
                     xp += G;
                     xo = *xp;                                 // next pass (the tables end with one pass of padding steps)
-                    amajor_blocks<A, R, SU, DT>(init, e, wp, acc);
+                    select_blocks<A, R, SU, DT>(lo0, lo2, wp, G, acc);
                     wp += wstep;
                 }
             };
             if constexpr (SIMPLE) {
                 run_row();
-                QK_UNROLL
-                for (int j = 0; j < SU; ++j)
-                    if (valid[j] && k < p.K) amajor_store<A, R>(p, acc[j], o + j * out_stride + k, oa + j * out_stride + k);
+                if (k < p.K) {
+                    QK_UNROLL
+                    for (int j = 0; j < SU; ++j)
+                        if (ls + j * SPC < nsamp) amajor_store<A, R>(p, acc[j], out_t, amps_t, o + j * out_stride + k);
+                }
             } else {
                 for (int b = k; b < p.brows * G_k; b += G_k) {
                     run_row();
@@ -324,7 +379,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
                     QK_UNROLL
                     for (int j = 0; j < SU; ++j) {
                         for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[j], shfl_xor_amp(acc[j], m));
-                        if (valid[j] && r == 0 && b < p.K) amajor_store<A, R>(p, acc[j], o + j * out_stride + b, oa + j * out_stride + b);
+                        if (ls + j * SPC < nsamp && r == 0 && b < p.K) amajor_store<A, R>(p, acc[j], out_t, amps_t, o + j * out_stride + b);
                     }
                 }
             }
@@ -333,17 +388,108 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
     }
 }
 
-// Window kernel: wide input rows (N784 K10: 6.3 KB of x, 19 KB of rotation triples per sample).  The triples of
-// a sample are built per ROW STEP from the step's input window (block_window) instead of once per sample, so a
-// CTA keeps tile * (W + 1) triples instead of tile * (N + 1) and shared memory no longer limits the resident
-// warps.  x is read straight from global memory (each input once per row step that uses it: twice at most, at
-// window boundaries).  One sample per lane at a time.
+// Direct kernel: layers whose output row b reads ONE input element, x[b N / K] (K a multiple of N: 4x4, 8x8,
+// 16x16, 4x8, ... with K a power of two <= 32, one lane per row).  The lane loads that element itself (coalesced:
+// the K lanes of a sample read N / K-strided neighbours), runs its CHEB sequence in registers and applies SELECT to
+// its row's N (D + 1) blocks - no shared memory, no barriers, no tiles; SU samples per lane share the SELECT
+// entries, and the next chunk's inputs are loaded while the current one is evaluated.  An element read by K / N
+// rows is evaluated by each of them (K evaluations per sample instead of N).
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+__global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const BlockParams p) {
+    constexpr int D1 = DT + 1;
+    const int G = p.G, SPC = p.SPC;
+    const int tid = threadIdx.x;
+    const int k = tid & (G - 1);                             // the lane's output row
+    const int slot = tid >> p.g_k_log2;                      // sample slot inside the CTA
+    if (k >= p.K) return;                                    // no cross-lane step in this kernel: idle lanes leave
+    const int nk = (int)(((long long)k * p.N) / p.K);        // the row's input element (ChebyshevStep.py:64, QKANLayer.py:132)
+    const bool counts = ((long long)k * p.N) % p.K == 0;     // the first row that reads an element reports its range violation
+    const CS<R>* __restrict__ wrow = reinterpret_cast<const CS<R>*>(p.cstab) + k;
+    const size_t wstep = (size_t)G * D1;                      // table entries between consecutive a of a lane
+
+    A init[4];
+    QK_UNROLL
+    for (int q = 0; q < 4; ++q) {
+        init[q].re = (R)p.init[2 * q];
+        if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
+    }
+    // a CTA iteration takes a chunk of SU * SPC consecutive samples: lane (slot, k) owns samples slot + j SPC of the chunk.
+    // Running pointers / counters (64-bit adds once per chunk, 32-bit offsets inside)
+    const long long chunk = (long long)SU * SPC;
+    const long long first = (long long)blockIdx.x * chunk + slot;          // the lane's first sample
+    const long long adv = (long long)gridDim.x * chunk;
+    long long left = p.B - first;                             // samples from the lane's current first one to the end of the batch
+    const double* __restrict__ xq = p.x + first * p.N + nk;
+    double* __restrict__ oq = p.outs[0] + (p.row0 + first) * p.K + k;
+    Cplx<R>* const aq = reinterpret_cast<Cplx<R>*>(p.amps);
+    long long eoff = 0;                                       // result elements advanced since the lane's first chunk
+    const long long xadv = adv * p.N, oadv = adv * p.K;
+    const int xstride = SPC * p.N, ostride = SPC * p.K;
+    const bool plain = p.plain != 0;
+    unsigned bad = 0;
+
+    double xn[SU];
+    QK_UNROLL
+    for (int j = 0; j < SU; ++j) xn[j] = ((long long)j * SPC < left) ? xq[j * xstride] : 0.0;
+    for (; left > 0; left -= adv, oq += oadv, eoff += oadv) {
+        double xv[SU];
+        QK_UNROLL
+        for (int j = 0; j < SU; ++j) xv[j] = xn[j];
+        xq += xadv;
+        {   // next chunk's inputs: in flight during this chunk's arithmetic
+            const long long nleft = left - adv;
+            if (nleft > (long long)(SU - 1) * SPC) {
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) xn[j] = xq[j * xstride];
+            } else {
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) xn[j] = ((long long)j * SPC < nleft) ? xq[j * xstride] : 0.0;
+            }
+        }
+        const bool full = left > (long long)(SU - 1) * SPC;   // every sample of the lane's share exists
+        A lo0[SU], lo2[SU], acc[SU];
+        QK_UNROLL
+        for (int j = 0; j < SU; ++j) {
+            // range count (the reference prints a warning, ChebyshevStep.py:46-49), clip (:52), CHEB sequence of the element
+            const double v = xv[j];
+            if ((!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) && counts && (full || (long long)j * SPC < left)) ++bad;
+            cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
+            set_amp(acc[j], 0.0);
+        }
+        // SELECT on the row's N (D + 1) blocks; UNPREPARE + SUM + post-selection is the lane's running sum
+        const CS<R>* wp = wrow;
+        for (int a = 0; a < p.N; ++a, wp += wstep) select_blocks<A, R, SU, DT>(lo0, lo2, wp, G, acc);
+        if (plain && full) {
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j) oq[j * ostride] = (double)acc[j].re * p.out_scale;
+        } else {
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j)
+                if ((long long)j * SPC < left) {
+                    store_result(p, (p.row0 + first) * p.K + k + eoff + j * ostride, (double)acc[j].re * p.out_scale);
+                    if (aq) {                                 // amplitudes are local: no row offset
+                        Cplx<R> z;
+                        z.re = (R)((double)acc[j].re * p.amp_scale);
+                        if constexpr (A::is_complex) z.im = (R)((double)acc[j].im * p.amp_scale);
+                        else z.im = R(0);
+                        aq[first * p.K + k + eoff + j * ostride] = z;
+                    }
+                }
+        }
+    }
+    if (bad) atomicAdd(p.oor, (unsigned long long)bad);
+}
+
+// Window kernel: wide input rows (N784 K10: 6.3 KB of x per sample).  The (lo0, lo2) entries of a sample are built
+// per ROW STEP from the step's input window (block_window) instead of once per sample, so a CTA keeps
+// tile * 2 (W + 1) amplitudes instead of tile * 2 (N + 1) and shared memory no longer limits the resident warps.
+// x is read straight from global memory (each input once per row step that uses it: twice at most, at window
+// boundaries, where its CHEB sequence is evaluated twice).  One sample per lane at a time.
 template <class A, typename R, int NT, int MINB, int DT>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(const BlockParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int G = p.G, G_r = p.G_r;
-    const int SPC = p.SPC, tile = p.tile, RB = p.row_bytes, W = p.window;
-    constexpr size_t ENTB = sizeof(TanEntry<R>);
+    const int SPC = p.SPC, tile = p.tile, RB = p.row_bytes, W = p.window, plane = p.plane_bytes;
     constexpr int D1 = DT + 1;
     char* cs = reinterpret_cast<char*>(smem_raw);
     const int tid = threadIdx.x;
@@ -354,18 +500,19 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(cons
     const CS<R>* __restrict__ wtab = reinterpret_cast<const CS<R>*>(p.cstab);
     const int* __restrict__ xotab = p.xotab;
 
-    for (int i = tid; i < tile; i += NT)                      // the dummy entries never change
-        *reinterpret_cast<TanEntry<R>*>(cs + (size_t)i * RB + W * ENTB) = tan_entry<R>(R(0), DT);
     A init[4];
     QK_UNROLL
     for (int q = 0; q < 4; ++q) {
         init[q].re = (R)p.init[2 * q];
         if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
     }
-    QK_UNROLL
-    for (int q = 0; q < 4; ++q) {
-        keep_in_register(init[q].re);
-        if constexpr (A::is_complex) keep_in_register(init[q].im);
+    {   // the dummy entries (x = 0) never change
+        A d0, d2;
+        cheb_element<A, R, DT>(init, R(0), d0, d2);
+        for (int i = tid; i < tile; i += NT) {
+            *reinterpret_cast<A*>(cs + (size_t)i * RB + W * sizeof(A)) = d0;
+            *reinterpret_cast<A*>(cs + (size_t)i * RB + plane + W * sizeof(A)) = d2;
+        }
     }
     const long long n_it = (p.B + tile - 1) / tile;
     const size_t step_steps = (size_t)p.passes * G;           // table steps of one row step
@@ -374,14 +521,16 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(cons
     for (long long it = blockIdx.x; it < n_it; it += gridDim.x) {
         const long long s0 = it * tile;
         const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
-        const int nsub = (nsamp + SPC - 1) / SPC;
+        const int ls_end = (nsamp + SPC - 1) & ~(SPC - 1);    // whole sub-iterations: the butterfly needs every lane
+        double* const out_t = p.outs[0] + (p.row0 + s0) * p.K;
+        void* const amps_t = p.amps ? (void*)(reinterpret_cast<Cplx<R>*>(p.amps) + s0 * p.K) : nullptr;
         int prev_hi = -1;
         for (int bi = 0; bi < p.brows; ++bi) {
             int lo, len;
             block_window(p.N, p.K, p.g_k_log2, bi, &lo, &len);
             __syncthreads();                                  // the previous row step's entries are consumed
             // pre-pass over the window of every sample of the tile (flat walk, no division in the loop): range count
-            // (ChebyshevStep.py:46-49; an input shared by two windows is counted once), clip (:52), triple
+            // (ChebyshevStep.py:46-49; an input shared by two windows is counted once), clip (:52), CHEB sequence
             unsigned bad = 0;
             {
                 const int n_in = nsamp * len;
@@ -391,7 +540,10 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(cons
                 for (int e = tid; e < n_in; e += NT) {
                     const double v = xw[(size_t)row * p.N + j];
                     if (lo + j > prev_hi && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
-                    *reinterpret_cast<TanEntry<R>*>(cs + (size_t)row * RB + j * ENTB) = tan_entry<R>(clip_unit<R>(v), DT);
+                    A lo0, lo2;
+                    cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0, lo2);
+                    *reinterpret_cast<A*>(cs + (size_t)row * RB + j * sizeof(A)) = lo0;
+                    *reinterpret_cast<A*>(cs + (size_t)row * RB + plane + j * sizeof(A)) = lo2;
                     j += dj;
                     row += dr;
                     if (j >= len) { j -= len; ++row; }
@@ -402,29 +554,30 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(cons
             __syncthreads();
 
             const int b = (bi << p.g_k_log2) + k;
-            const CS<R>* wp0 = wtab + ((size_t)bi * step_steps + g) * D1;
+            const CS<R>* wp0 = wtab + (size_t)bi * step_steps * D1 + g;
             const int* xp0 = xotab + (size_t)bi * step_steps + g;
             const int x0 = xp0[0];
-            int ls = slot;
-            for (int si = 0; si < nsub; ++si, ls += SPC) {
+            for (int ls = slot; ls < ls_end; ls += SPC) {
                 const char* row = cs + (size_t)ls * RB;       // idle slots of a ragged tile evolve a stale row; nothing is stored
                 const CS<R>* wp = wp0;
                 const int* xp = xp0;
-                int xo = x0;
-                A acc[1];
+                int xo = x0, xprev = -1;
+                A acc[1], lo0[1], lo2[1];
                 set_amp(acc[0], 0.0);
                 for (int pi = 0; pi < p.passes; ++pi) {
-                    TanEntry<R> e[1];
-                    e[0] = *reinterpret_cast<const TanEntry<R>*>(row + xo);
+                    if (xo != xprev) {
+                        lo0[0] = *reinterpret_cast<const A*>(row + xo);
+                        lo2[0] = *reinterpret_cast<const A*>(row + plane + xo);
+                        xprev = xo;
+                    }
                     xp += G;
                     xo = *xp;                                 // next pass (the tables end with one pass of padding steps)
-                    amajor_blocks<A, R, 1, DT>(init, e, wp, acc);
+                    select_blocks<A, R, 1, DT>(lo0, lo2, wp, G, acc);
                     wp += wstep;
                 }
                 // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
                 for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[0], shfl_xor_amp(acc[0], m));
-                if (ls < nsamp && r == 0 && b < p.K)
-                    amajor_store<A, R>(p, acc[0], (p.row0 + s0 + ls) * p.K + b, (s0 + ls) * p.K + b);
+                if (ls < nsamp && r == 0 && b < p.K) amajor_store<A, R>(p, acc[0], out_t, amps_t, ls * p.K + b);
             }
         }
     }
@@ -450,22 +603,24 @@ cudaError_t launch_amajor_impl(const BlockParams& p0, int G, int sm_count, cudaS
     auto kern = qkan_block_amajor_kernel<A, R, SU, NT, MINB, SIMPLE, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
-    p.row_bytes = tan_row_words(p.N, G, (int)sizeof(R)) * (int)sizeof(R);
-    if (const char* e = getenv("QKAN_BLOCK_ROW_WORDS")) {      // tuning aid
-        if (atoi(e) >= 3 * (p.N + 1)) p.row_bytes = atoi(e) * (int)sizeof(R);
+    p.row_bytes = amajor_row_amps(p.N + 1, G, (int)sizeof(A)) * (int)sizeof(A);
+    p.plane_bytes = (p.N + 1) * (int)sizeof(A);
+    if (const char* e = getenv("QKAN_BLOCK_ROW_AMPS")) {       // tuning aid
+        if (atoi(e) >= 2 * (p.N + 1)) p.row_bytes = atoi(e) * (int)sizeof(A);
     }
     // wide rows: staging the raw x twice more than doubles the shared memory per sample and would
     // halve the resident warps; the per-tile compute is long, so the pre-pass reads global memory directly
     p.direct_x = amajor_direct_x(SPC, p.N) ? 1 : 0;
     auto smem_for = [&](int sub) { return amajor_smem_bytes(p.N, SPC, p.row_bytes, SU, sub); };
     int sub = (int)(8192 / ((size_t)SPC * p.N * 8));          // about 8 KiB of x per tile ...
-    const int sub_cs = (int)(49152 / ((size_t)SPC * p.row_bytes));   // ... and at most 48 KiB of triples
+    const int sub_cs = (int)(49152 / ((size_t)SPC * p.row_bytes));   // ... and at most 48 KiB of block amplitudes
     if (sub > sub_cs) sub = sub_cs;
     if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
     // a lane takes SU sub-iterations at a time: a tile of an odd number of them would leave a sample slot idle
     auto round_su = [](int v) { v -= v % SU; return v < SU ? SU : v; };
     sub = round_su(sub);
+    while (sub > SU && smem_for(sub) > AMAJOR_SMEM_CAP) sub = round_su(sub - SU);
     if (smem_for(sub) > AMAJOR_SMEM_CAP) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(sub));
     if (e != cudaSuccess) return e;
@@ -512,12 +667,44 @@ BlockKernelInfo make_amajor_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = 0; k.U = 1; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 1; k.window = 0; k.amajor = 1;
+    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_amajor<A, R, SU, NT, MINB, DT>;
     return k;
 }
 
-inline size_t amajor_window_smem_bytes(int SPC, int row_bytes, int sub) { return (size_t)SPC * sub * row_bytes; }
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+cudaError_t launch_direct(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p0.D != DT || p0.g_r_log2 != 0 || p0.brows != 1 || p0.K % p0.N != 0) return cudaErrorInvalidValue;
+    auto kern = qkan_block_direct_kernel<A, R, SU, NT, MINB, DT>;
+    BlockParams p = p0;
+    const int SPC = NT / G;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const long long chunk = (long long)SU * SPC;
+    const long long n_chunks = (p.B + chunk - 1) / chunk;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > n_chunks) grid = n_chunks;
+    if (grid < 1) grid = 1;
+    p.sub = SU; p.tma_ok = 0; p.direct_x = 1; p.s_tot = -1;
+    p.G = G; p.G_r = 1; p.G_k = G;
+    p.SPC = SPC; p.tile = (int)chunk;
+    p.row_bytes = 0; p.plane_bytes = 0;
+    if (grid_out) *grid_out = (int)grid;
+    if (smem_out) *smem_out = 0;
+    kern<<<(unsigned)grid, NT, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+BlockKernelInfo make_direct_info(int is_default) {
+    BlockKernelInfo k;
+    k.amp = AmpId<A>::v;
+    k.mode = 0; k.U = 1; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
+    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 1; k.amp_bytes = (int)sizeof(A);
+    k.launch = &launch_direct<A, R, SU, NT, MINB, DT>;
+    return k;
+}
 
 template <class A, typename R, int NT, int MINB, int DT>
 cudaError_t launch_amajor_window(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
@@ -525,12 +712,14 @@ cudaError_t launch_amajor_window(const BlockParams& p0, int G, int sm_count, cud
     auto kern = qkan_block_amajor_window_kernel<A, R, NT, MINB, DT>;
     BlockParams p = p0;
     const int SPC = NT / G;
-    p.row_bytes = tan_row_words(p.window, G, (int)sizeof(R)) * (int)sizeof(R);
-    int sub = (int)(32768 / ((size_t)SPC * p.row_bytes));      // about 32 KiB of rotation triples per CTA
+    p.row_bytes = amajor_row_amps(p.window + 1, G, (int)sizeof(A)) * (int)sizeof(A);
+    p.plane_bytes = (p.window + 1) * (int)sizeof(A);
+    int sub = (int)(32768 / ((size_t)SPC * p.row_bytes));      // about 32 KiB of block amplitudes per CTA
     if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
     if (sub > 32) sub = 32;
     if (sub < 1) sub = 1;
     auto smem_for = [&](int sb) { return amajor_window_smem_bytes(SPC, p.row_bytes, sb); };
+    while (sub > 1 && smem_for(sub) > AMAJOR_SMEM_CAP) --sub;
     if (smem_for(sub) > AMAJOR_SMEM_CAP) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(sub));
     if (e != cudaSuccess) return e;
@@ -557,7 +746,7 @@ BlockKernelInfo make_amajor_window_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = 0; k.U = 1; k.SU = 1; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 1; k.window = 1; k.amajor = 1;
+    k.tan = 1; k.window = 1; k.amajor = 1; k.direct = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_amajor_window<A, R, NT, MINB, DT>;
     return k;
 }

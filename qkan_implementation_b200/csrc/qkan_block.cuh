@@ -151,7 +151,9 @@ struct BlockParams {
     int G, G_r, G_k;            // lanes per sample / per row / rows in parallel
     int SPC, tile;              // samples in flight per CTA; samples per x tile (SPC * sub)
     int row_bytes;              // cs row stride: N + 1 entries, padded so that the lanes of one shared-memory
-                                // phase (128 bytes) hit different banks (see cs_row_stride / tan_row_words)
+                                // phase (128 bytes) hit different banks (see cs_row_stride / amajor_row_amps)
+    int plane_bytes;            // a-major kernels: offset of the lo2 plane inside a cs row
+    int plain;                  // a-major kernels: results go to outs[0] only (no peers, no multicast, no amplitudes)
     long long s_tot;            // sub-iterations (SPC samples each) of the batch; CTA c of g owns the contiguous run
                                 // [c s_tot / g, (c+1) s_tot / g): sizes differ by at most one sub-iteration, so there
                                 // is no tail imbalance from whole tiles
@@ -671,6 +673,8 @@ struct BlockKernelInfo {
     int tan;                    // scaled-rotation form: cs rows hold (t, alpha, beta) triples (qkan_amajor.cuh)
     int window;                 // window kernel (wide input rows): entries are built per row step
     int amajor;                 // a-major tables (qkan_amajor.cuh): D + 1 SELECT entries per (row step, pass, lane)
+    int amp_bytes;              // a-major kernels: sizeof(amplitude), the entry size of the cs planes
+    int direct;                 // direct kernel (qkan_amajor.cuh): every output row reads one input element, no shared memory
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
@@ -747,7 +751,7 @@ BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 0; k.window = 0; k.amajor = 0;
+    k.tan = 0; k.window = 0; k.amajor = 0; k.direct = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
     return k;
 }

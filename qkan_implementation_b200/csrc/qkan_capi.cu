@@ -79,6 +79,12 @@ struct qkan_layer {
     cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {};
     cudaEvent_t ev_w = nullptr;               // recorded after the table build of set_weights: the host path's own
                                               // (non-blocking) streams wait on it, whatever stream the caller used
+    // host-buffer path: the chunk pipeline (copies + kernels of one call) captured as a CUDA graph, replayed while the
+    // caller keeps passing the same buffers (one launch instead of ~7 enqueue calls per chunk)
+    struct HostKey { const void* x; void* out; void* amps; int64_t B; int in_direct, out_direct, nchunk; };
+    HostKey last_key{}, graph_key{};
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join_in = nullptr, ev_join_out = nullptr;
 };
 
 static size_t amp_real_size(int dtype) { return dtype == QKAN_COMPLEX64 ? 4 : 8; }
@@ -103,15 +109,17 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         const char* tune = getenv("QKAN_BLOCK_TUNE");          // tuning aid: "U:NT:MINB:SU" (0 = any)
         int fU = 0, fNT = 0, fMINB = 0, fSU = 0;
         if (tune) sscanf(tune, "%d:%d:%d:%d", &fU, &fNT, &fMINB, &fSU);
-        const size_t rsz = amp_real_size(dtype);
+        const int asz = dtype == QKAN_COMPLEX128 ? 16 : 8;     // sizeof(amplitude): complex128 16, complex64 8, real64 8
         // ---- a-major scaled-rotation kernels (qkan_amajor.cuh): compat mode, 1 <= D <= 16
         const bool amajor_ok = mode == QKAN_MODE_COMPAT && max_degree >= TAN_MIN_DT && max_degree <= TAN_MAX_DT &&
                                fU <= 1 && !getenv("QKAN_BLOCK_NO_DT");
         // two samples per lane share every SELECT entry and the per-pass bookkeeping: pays for shallow sequences
-        const int want_SU = fSU ? fSU : 2;
-        auto find_amajor = [&](int NT, int SU, bool window_kernel) -> const BlockKernelInfo* {
+        const int want_SU = fSU ? fSU : 2;                     // tile kernel
+        const int want_SU_direct = fSU ? fSU : 4;              // direct kernel (profiles/r02e_tune_direct.jsonl)
+        auto find_amajor = [&](int NT, int SU, bool window_kernel, bool direct_kernel = false) -> const BlockKernelInfo* {
             for (const BlockKernelInfo& k : block_registry()) {
-                if (!k.amajor || (k.window != 0) != window_kernel || k.amp != dtype || k.DT != max_degree || k.NT != NT) continue;
+                if (!k.amajor || (k.window != 0) != window_kernel || (k.direct != 0) != direct_kernel || k.amp != dtype ||
+                    k.DT != max_degree || k.NT != NT) continue;
                 if (!window_kernel && k.SU != SU) continue;
                 if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
                 return &k;
@@ -120,6 +128,20 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         };
         // resident warps per SM that the shared memory of one CTA allows (registers cap it at 32 / 24)
         auto warps_for = [](size_t smem, int NT) { return (int)((220 * 1024 / (smem + 1024)) * (size_t)(NT / 32)); };
+        // rows that read a single input element: the direct kernel (no shared memory)
+        if (amajor_ok && !getenv("QKAN_BLOCK_NO_DIRECT") && !getenv("QKAN_BLOCK_FORCE_WINDOW")) {
+            const BlockLayout cand = plan_amajor_layout(N, K, 0);
+            if (amajor_direct_ok(N, K, cand)) {
+                const int NTs[2] = {256, 128};
+                for (int ni = 0; ni < 2 && !bbest; ++ni) {
+                    if (fNT && NTs[ni] != fNT) continue;
+                    for (int SU = want_SU_direct; SU >= 1 && !bbest; SU >>= 1) {
+                        const BlockKernelInfo* k = find_amajor(NTs[ni], SU, false, true);
+                        if (k) { bbest = k; lay = cand; }
+                    }
+                }
+            }
+        }
         // pass 0 wants >= 24 resident warps (the FP64 pipe needs them to stay busy), pass 1 takes whatever launches
         for (int pass = 0; pass < 2 && amajor_ok && !bbest; ++pass) {
             const int NTs[2] = {256, 128};
@@ -131,7 +153,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                     const int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                     if (G < (1 << min_g) || G > NT) continue;
                     const int SPC = NT / G;
-                    const int row_bytes = tan_row_words(N, G, (int)rsz) * (int)rsz;
+                    const int row_bytes = amajor_row_amps(N + 1, G, asz) * asz;
                     for (int SU = want_SU; SU >= 1 && !bbest; --SU) {
                         const size_t smem = amajor_smem_bytes(N, SPC, row_bytes, SU, SU);     // smallest tile the launch can use
                         if (smem > AMAJOR_SMEM_CAP || (pass == 0 && warps_for(smem, NT) < 24)) continue;
@@ -152,7 +174,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 const int G = 1 << (c.g_r_log2 + c.g_k_log2);
                 if (G < (1 << mg) || c.efficiency < 0.9) continue;
                 const int W = block_window_max(N, K, c.g_k_log2, c.brows);
-                const size_t win_cs = amajor_window_smem_bytes(256 / G, tan_row_words(W, G, (int)rsz) * (int)rsz, 1);
+                const size_t win_cs = amajor_window_smem_bytes(256 / G, amajor_row_amps(W + 1, G, asz) * asz, 1);
                 if (win_cs > AMAJOR_SMEM_CAP || warps_for(win_cs, 256) < want) continue;
                 const BlockKernelInfo* k = find_amajor(256, 1, true);
                 if (k) { bbest = k; lay = c; window = W; }
@@ -167,7 +189,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 BlockLayout cand = plan_block_layout(N, K, max_degree, min_g, fU);
                 int G = 1 << (cand.g_r_log2 + cand.g_k_log2);
                 if (G < (1 << min_g) || G > NT) continue;
-                auto cs_bytes_for = [&](int) { return (size_t)(NT / G) * (N + 1) * 2 * rsz; };
+                auto cs_bytes_for = [&](int) { return (size_t)(NT / G) * (N + 1) * 2 * amp_real_size(dtype); };
                 // wide input rows: shared memory limits the resident warps (< 24 per SM), so keep four blocks
                 // per lane in flight instead of one (measured on N784 K10 D5: 3.7 -> 4.0 M samples/s)
                 if (!fU && (220 * 1024 / (cs_bytes_for(cand.U) + 1024)) * (size_t)(NT / 32) < 24) {
@@ -187,8 +209,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
             }
         }
         if (getenv("QKAN_DEBUG_SELECT") && bbest)
-            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> amajor=%d U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
-                    N, K, max_degree, dtype, bbest->amajor, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
+            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> direct=%d amajor=%d U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
+                    N, K, max_degree, dtype, bbest->direct, bbest->amajor, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
                     lay.g_r_log2, lay.g_k_log2, lay.passes, lay.brows);
         if (!bbest) {
             char buf[160];
@@ -265,6 +287,10 @@ extern "C" void qkan_layer_destroy(qkan_layer* l) {
         if (l->ev_k[i]) cudaEventDestroy(l->ev_k[i]);
     }
     if (l->ev_w) cudaEventDestroy(l->ev_w);
+    if (l->graph) cudaGraphExecDestroy(l->graph);
+    if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+    if (l->ev_join_in) cudaEventDestroy(l->ev_join_in);
+    if (l->ev_join_out) cudaEventDestroy(l->ev_join_out);
     delete l;
 }
 
@@ -283,11 +309,11 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
         const unsigned nt = 128, nb = (unsigned)((steps + nt - 1) / nt);
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_amajor_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
-                                                                            l->lay.g_r_log2, l->lay.g_k_log2, 12, l->window, steps,
+                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, l->window, steps,
                                                                             (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_amajor_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
-                                                                             l->lay.g_r_log2, l->lay.g_k_log2, 24, l->window, steps,
+                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, l->window, steps,
                                                                              (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else if (l->engine == 0) {
         const long long G = 1ll << (l->lay.g_r_log2 + l->lay.g_k_log2);
@@ -346,6 +372,8 @@ static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, voi
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
         p.sub = 1; p.tma_ok = 0; p.direct_x = 0; p.window = l->window;
+        p.plane_bytes = 0;
+        p.plain = (p.n_out == 1 && !p.mc_out && !amps) ? 1 : 0;
         for (int q = 0; q < 8; ++q) p.init[q] = 0.0;
         p.init[0] = 1.0;                                   // PREPARE'd block state (1, 0, 0, 0), un-normalised
         p.out_scale = 1.0 / ((double)l->N * (double)(l->D + 1));
@@ -438,40 +466,46 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     if (B == 0) return QKAN_OK;
     if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
     CU(cudaSetDevice(l->device));
-    // Pinned (page-locked, device-mapped) host buffers: no staging copies at all.  The kernel streams x from
-    // host memory itself (the same 1-D TMA bulk loads, two tiles in flight per CTA) and stores every result
-    // straight into the host buffer, so input and output cross PCIe concurrently with the arithmetic and there is
-    // no chunk pipeline to fill and drain.  Pageable buffers take the staged path below.
-    {
-        auto mapped = [](const void* ptr, void** dev) -> bool {
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
-            if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
-            *dev = at.devicePointer;
-            return true;
-        };
-        void *dx = nullptr, *dout = nullptr, *damps = nullptr;
-        const char* mode_env = getenv("QKAN_HOST_PATH");          // "staged" forces the copy pipeline (A/B aid)
-        const bool want_zero_copy = !(mode_env && strcmp(mode_env, "staged") == 0);
-        if (want_zero_copy && mapped(x, &dx) && mapped(out, &dout) && (!amps || mapped(amps, &damps))) {
-            if (!l->s_k) {
-                int rc0 = ensure_host_path(l, 0, false);
-                if (rc0) return rc0;
-            }
-            if (l->ev_w) CU(cudaStreamWaitEvent(l->s_k, l->ev_w, 0));
-            int rc = launch_on(l, (const double*)dx, B, (double*)dout, damps, l->s_k);
-            if (rc) return rc;
-            CU(cudaStreamSynchronize(l->s_k));
-            return QKAN_OK;
-        }
+    // Pinned (page-locked, device-mapped) host buffers can be used by the kernel directly: it streams x from host memory
+    // itself and / or stores every result straight into the host buffer, so that side needs no staging copy and crosses
+    // PCIe concurrently with the arithmetic.  Each side is either "direct" (kernel access) or "copy" (chunked
+    // cudaMemcpyAsync on its own stream, overlapped with the kernels of the neighbouring chunks):
+    //   QKAN_HOST_PATH = copy_in (copy, direct; default for pinned buffers) | zero_copy (direct, direct) | staged (copy,
+    //   copy; always for pageable buffers) | copy_out (direct, copy)
+    // Measured on B200 / PCIe 5 (profiles/r02g_e2e_ab.txt, r02f_pcie_probe_n1.txt): the DMA engines move 55 GB/s one way and
+    // 47 GB/s each way when both directions run; SM-issued reads reach 50 GB/s alone but reads + writes together only
+    // 38 GB/s each way.  DMA reads + SM writes is the best combination on the balanced N4 K4 shape (0.855 ms against 0.873
+    // zero-copy and 0.90 staged per 1M samples) and within 2 % of the best on the input-heavy N784 K10 shape (12.0 ms
+    // against 14.9 zero-copy).
+    auto mapped = [](const void* ptr, void** dev) -> bool {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+        *dev = at.devicePointer;
+        return true;
+    };
+    void *dx = nullptr, *dout = nullptr, *damps = nullptr;
+    const bool x_mapped = mapped(x, &dx);
+    const bool out_mapped = mapped(out, &dout) && (!amps || mapped(amps, &damps));
+    bool in_direct = false, out_direct = out_mapped;
+    if (const char* m = getenv("QKAN_HOST_PATH")) {
+        if (strcmp(m, "staged") == 0) { in_direct = false; out_direct = false; }
+        else if (strcmp(m, "zero_copy") == 0) { in_direct = x_mapped; }
+        else if (strcmp(m, "copy_out") == 0) { in_direct = x_mapped; out_direct = false; }
     }
-    int rc = ensure_host_path(l, B, amps != nullptr);
+    int rc = ensure_host_path(l, (in_direct && out_direct) ? 0 : B, amps != nullptr && !out_direct);
     if (rc) return rc;
     if (l->ev_w) CU(cudaStreamWaitEvent(l->s_k, l->ev_w, 0));
-    // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile
-    // ~16 MiB of traffic per chunk: 4 chunks for 1M x (4 in + 4 out) doubles measured best on B200 / PCIe 5
-    // (profiles/r01_e2e_chunks.txt): fewer chunks expose fill / drain, more add launch and copy overhead
-    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 24);
+    if (in_direct && out_direct) {                           // one launch on the host pointers
+        rc = launch_on(l, (const double*)dx, B, (double*)dout, damps, l->s_k);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(l->s_k));
+        return QKAN_OK;
+    }
+    // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile.  About 8 MiB of traffic per
+    // chunk (8 chunks for 1M x (4 in + 4 out) doubles): the first copy-in is not overlapped, so fewer chunks expose the
+    // fill, while each DMA copy carries ~10 us of fixed cost, so many small chunks are slower (16: +9 %, 64: +60 %)
+    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 23);
     if (const char* e = getenv("QKAN_HOST_CHUNKS")) nchunk = atoi(e);   // tuning aid
     if (nchunk < 1) nchunk = 1;
     if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
@@ -479,25 +513,88 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     const int64_t spi = l->engine == 0 ? (l->bkern->NT >> (l->lay.g_r_log2 + l->lay.g_k_log2)) : l->kern->spi;
     per = (per + spi - 1) / spi * spi;
     const size_t asz = 2 * amp_real_size(l->dtype);
-    int i = 0;
-    for (int64_t off = 0; off < B; off += per, ++i) {
-        const int64_t n = (B - off < per) ? (B - off) : per;
-        CU(cudaMemcpyAsync(l->d_x + off * l->N, x + off * l->N, (size_t)n * l->N * sizeof(double),
-                           cudaMemcpyHostToDevice, l->s_in));
-        CU(cudaEventRecord(l->ev_in[i], l->s_in));
-        CU(cudaStreamWaitEvent(l->s_k, l->ev_in[i], 0));
-        rc = launch_on(l, l->d_x + off * l->N, n, l->d_out + off * l->K,
-                       amps ? (char*)l->d_amps + (size_t)off * l->K * asz : nullptr, l->s_k);
-        if (rc) return rc;
-        CU(cudaEventRecord(l->ev_k[i], l->s_k));
-        CU(cudaStreamWaitEvent(l->s_out, l->ev_k[i], 0));
-        CU(cudaMemcpyAsync(out + off * l->K, l->d_out + off * l->K, (size_t)n * l->K * sizeof(double),
-                           cudaMemcpyDeviceToHost, l->s_out));
-        if (amps)
-            CU(cudaMemcpyAsync((char*)amps + (size_t)off * l->K * asz, (char*)l->d_amps + (size_t)off * l->K * asz,
-                               (size_t)n * l->K * asz, cudaMemcpyDeviceToHost, l->s_out));
+    auto enqueue = [&]() -> int {
+        int i = 0;
+        for (int64_t off = 0; off < B; off += per, ++i) {
+            const int64_t n = (B - off < per) ? (B - off) : per;
+            const double* xin = (const double*)dx + off * l->N;
+            if (!in_direct) {
+                CU(cudaMemcpyAsync(l->d_x + off * l->N, x + off * l->N, (size_t)n * l->N * sizeof(double),
+                                   cudaMemcpyHostToDevice, l->s_in));
+                CU(cudaEventRecord(l->ev_in[i], l->s_in));
+                CU(cudaStreamWaitEvent(l->s_k, l->ev_in[i], 0));
+                xin = l->d_x + off * l->N;
+            }
+            double* yout = out_direct ? (double*)dout + off * l->K : l->d_out + off * l->K;
+            void* aout = !amps ? nullptr : (out_direct ? (void*)((char*)damps + (size_t)off * l->K * asz)
+                                                       : (void*)((char*)l->d_amps + (size_t)off * l->K * asz));
+            int rcl = launch_on(l, xin, n, yout, aout, l->s_k);
+            if (rcl) return rcl;
+            if (!out_direct) {
+                CU(cudaEventRecord(l->ev_k[i], l->s_k));
+                CU(cudaStreamWaitEvent(l->s_out, l->ev_k[i], 0));
+                CU(cudaMemcpyAsync(out + off * l->K, l->d_out + off * l->K, (size_t)n * l->K * sizeof(double),
+                                   cudaMemcpyDeviceToHost, l->s_out));
+                if (amps)
+                    CU(cudaMemcpyAsync((char*)amps + (size_t)off * l->K * asz, (char*)l->d_amps + (size_t)off * l->K * asz,
+                                       (size_t)n * l->K * asz, cudaMemcpyDeviceToHost, l->s_out));
+            }
+        }
+        return QKAN_OK;
+    };
+    // CUDA graph of the pipeline: built on the second consecutive call with the same buffers, replayed afterwards.
+    // Pinned buffers only (copies from pageable memory are staged by the driver and cannot be captured usefully).
+    const qkan_layer::HostKey key{x, out, amps, B, in_direct ? 1 : 0, out_direct ? 1 : 0, nchunk};
+    auto same = [](const qkan_layer::HostKey& a, const qkan_layer::HostKey& b) {
+        return a.x == b.x && a.out == b.out && a.amps == b.amps && a.B == b.B && a.in_direct == b.in_direct &&
+               a.out_direct == b.out_direct && a.nchunk == b.nchunk;
+    };
+    const bool graph_ok = x_mapped && out_mapped && !getenv("QKAN_HOST_NO_GRAPH");
+    if (graph_ok && l->graph && same(key, l->graph_key)) {
+        CU(cudaGraphLaunch(l->graph, l->s_k));
+        CU(cudaStreamSynchronize(l->s_k));
+        return QKAN_OK;
     }
-    CU(cudaStreamSynchronize(l->s_out));
+    if (graph_ok && same(key, l->last_key)) {
+        if (l->graph) { cudaGraphExecDestroy(l->graph); l->graph = nullptr; }
+        if (!l->ev_fork) {
+            CU(cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&l->ev_join_in, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&l->ev_join_out, cudaEventDisableTiming));
+        }
+        CU(cudaStreamSynchronize(l->s_k));
+        CU(cudaStreamBeginCapture(l->s_k, cudaStreamCaptureModeThreadLocal));
+        // fork the copy streams into the capture, enqueue the pipeline, join them back
+        cudaError_t ce = cudaEventRecord(l->ev_fork, l->s_k);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(l->s_in, l->ev_fork, 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(l->s_out, l->ev_fork, 0);
+        int rcq = ce == cudaSuccess ? enqueue() : QKAN_ERR_CUDA;
+        if (ce == cudaSuccess) ce = cudaEventRecord(l->ev_join_in, l->s_in);
+        if (ce == cudaSuccess) ce = cudaEventRecord(l->ev_join_out, l->s_out);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(l->s_k, l->ev_join_in, 0);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent(l->s_k, l->ev_join_out, 0);
+        cudaGraph_t g = nullptr;
+        cudaError_t ee = cudaStreamEndCapture(l->s_k, &g);
+        if (rcq == QKAN_OK && ce == cudaSuccess && ee == cudaSuccess && g) {
+            ee = cudaGraphInstantiate(&l->graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ee == cudaSuccess) {
+                l->graph_key = key;
+                CU(cudaGraphLaunch(l->graph, l->s_k));
+                CU(cudaStreamSynchronize(l->s_k));
+                return QKAN_OK;
+            }
+            l->graph = nullptr;
+        } else if (g) {
+            cudaGraphDestroy(g);
+        }
+        cudaGetLastError();                                  // capture failed: fall through to the plain pipeline
+    }
+    l->last_key = key;
+    rc = enqueue();
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(l->s_k));
+    if (!out_direct) CU(cudaStreamSynchronize(l->s_out));
     return QKAN_OK;
 }
 
@@ -548,13 +645,26 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
         info->input_window = l->window;
         info->flops_per_block_basis = info->flops_exec;
         if (k.amajor) {
-            // a-major scaled-rotation kernels (amajor_blocks): per (a, b) ONE evolution of the block state - D-1 full
-            // passes of 8 FMA and the pruned last pass alpha u + beta v (4 MUL + 4 FMA) - then per degree copy the
-            // SELECT rotation fused with the read-out sum (4 FMA)
-            const double ab = (double)l->N * l->K;
+            // a-major scaled-rotation kernels (qkan_amajor.cuh).  Per input element the pre-pass runs the CHEB sequence
+            // once - D-1 full passes of 8 FMA and the pruned last pass alpha u + beta v (4 MUL + 4 FMA); the window
+            // kernel evaluates an element once per row step whose window holds it.  Per (a, b, d) block: the SELECT
+            // rotation fused with the read-out sum (4 FMA).  (The conversion of x into the rotation entry, one
+            // reciprocal square root per element, is not counted.)
+            double elems = (double)l->N;
+            if (k.direct) elems = (double)l->K;               // every row evaluates its own element
+            info->direct_rows = k.direct;
+            if (l->window) {
+                elems = 0.0;
+                for (int bi = 0; bi < l->lay.brows; ++bi) {
+                    int lo, len;
+                    block_window(l->N, l->K, l->lay.g_k_log2, bi, &lo, &len);
+                    elems += len;
+                }
+            }
             info->degree_factored = 1;
-            info->flops_exec = cf * ab * (16.0 * (Dd - 1.0) + 12.0 + 8.0 * (Dd + 1.0));
-            info->fp_inst_exec = cf * ab * (8.0 * Dd + 4.0 * (Dd + 1.0));
+            info->cheb_elements = (int)elems;
+            info->flops_exec = cf * (elems * (16.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
+            info->fp_inst_exec = cf * (elems * 8.0 * Dd + 4.0 * (double)info->blocks);
             info->flops_per_block_basis = cf * (double)info->blocks * (16.0 * Dd + 4.0);
         }
         info->layout_efficiency = l->lay.efficiency;

@@ -209,15 +209,24 @@ int emu_block(const double* x, const double* W, long long B, int N, int K, int D
     return 0;
 }
 
-// ---- a-major kernels (qkan_amajor.cuh): planner, tables, per-(a, b) evolution and read-out, lane by lane
-template <class A, typename R, int DT> struct AmajorRun {
-    static void go(int D, const A (&init)[4], const TanEntry<R> (&e)[1], const CS<R>* wp, A (&acc)[1]) {
-        if (D == DT) amajor_blocks<A, R, 1, DT>(init, e, wp, acc);
-        else AmajorRun<A, R, DT - 1>::go(D, init, e, wp, acc);
+// ---- a-major kernels (qkan_amajor.cuh): planner, tables, CHEB per input element, SELECT per block, read-out; lane by lane
+template <class A, typename R, int DT> struct ChebRun {
+    static void go(int D, const A (&init)[4], R c, A& lo0, A& lo2) {
+        if (D == DT) cheb_element<A, R, DT>(init, c, lo0, lo2);
+        else ChebRun<A, R, DT - 1>::go(D, init, c, lo0, lo2);
     }
 };
-template <class A, typename R> struct AmajorRun<A, R, 0> {
-    static void go(int, const A (&)[4], const TanEntry<R> (&)[1], const CS<R>*, A (&)[1]) {}
+template <class A, typename R> struct ChebRun<A, R, 0> {
+    static void go(int, const A (&)[4], R, A&, A&) {}
+};
+template <class A, typename R, int DT> struct SelectRun {
+    static void go(int D, const A (&lo0)[1], const A (&lo2)[1], const CS<R>* wp, int G, A (&acc)[1]) {
+        if (D == DT) select_blocks<A, R, 1, DT>(lo0, lo2, wp, G, acc);
+        else SelectRun<A, R, DT - 1>::go(D, lo0, lo2, wp, G, acc);
+    }
+};
+template <class A, typename R> struct SelectRun<A, R, 0> {
+    static void go(int, const A (&)[1], const A (&)[1], const CS<R>*, int, A (&)[1]) {}
 };
 
 // window != 0: the window kernel's tables and per-row-step input windows
@@ -234,25 +243,35 @@ int emu_amajor(const double* x, const double* W, long long B, int N, int K, int 
     std::vector<int> xotab(steps);
     for (long long e = 0; e < steps; ++e)
         fill_amajor_step<R>(e, W, N, K, D, lay.passes, lay.brows, lay.g_r_log2, lay.g_k_log2, wtab.data(), xotab.data(),
-                            (int)sizeof(TanEntry<R>), window);
+                            (int)sizeof(A), window);
     int NA = 0, NB = 0, L = 0;
     while ((1 << NA) < N) ++NA;
     while ((1 << NB) < K) ++NB;
     while ((1 << L) < D + 1) ++L;
     const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    A init[4];
+    for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
+    // a sample's cs row as the kernels lay it out: plane lo0[0 .. n1), plane lo2[0 .. n1), padded stride
+    const int n1 = (window ? window : N) + 1;
+    const int row_amps = amajor_row_amps(n1, G, (int)sizeof(A));
+    if (row_amps < 2 * n1) return -7;
+    const int plane = n1 * (int)sizeof(A);
     for (long long s = 0; s < B; ++s) {
-        std::vector<TanEntry<R>> cst((size_t)N + 1);
-        for (int n = 0; n <= N; ++n) cst[n] = tan_entry<R>(n < N ? clip_unit<R>(x[s * N + n]) : R(0), D);
+        std::vector<A> full0(N + 1), full2(N + 1);
+        for (int n = 0; n <= N; ++n) ChebRun<A, R, 16>::go(D, init, n < N ? clip_unit<R>(x[s * N + n]) : R(0), full0[n], full2[n]);
         for (int bi = 0; bi < lay.brows; ++bi) {
-            std::vector<TanEntry<R>> row = cst;
+            std::vector<A> row(row_amps);
+            for (auto& v : row) set_amp(v, 7.0);             // stale entries must never be read
             if (window) {                                    // the row step's window of the input row, dummy at index `window`
                 int lo, len;
                 block_window(N, K, lay.g_k_log2, bi, &lo, &len);
                 if (len > window) return -6;
-                row.assign((size_t)window + 1, TanEntry<R>{R(7), R(7), R(7)});   // stale entries must never be read
-                for (int j = 0; j < len; ++j) row[j] = cst[lo + j];
-                row[window] = cst[N];
+                for (int j = 0; j < len; ++j) { row[j] = full0[lo + j]; row[n1 + j] = full2[lo + j]; }
+                row[window] = full0[N]; row[n1 + window] = full2[N];
+            } else {
+                for (int n = 0; n <= N; ++n) { row[n] = full0[n]; row[n1 + n] = full2[n]; }
             }
+            const char* rowb = reinterpret_cast<const char*>(row.data());
             for (int k = 0; k < G_k; ++k) {
                 const int b = bi * G_k + k;
                 std::vector<A> acc(G_r);
@@ -262,11 +281,12 @@ int emu_amajor(const double* x, const double* W, long long B, int N, int K, int 
                     const int g = k * G_r + r;
                     for (int pi = 0; pi < lay.passes; ++pi) {
                         const size_t st = ((size_t)bi * lay.passes + pi) * G + g;
-                        TanEntry<R> e[1];
-                        e[0] = *reinterpret_cast<const TanEntry<R>*>(reinterpret_cast<const char*>(row.data()) + xotab[st]);
-                        A init[4];
-                        for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
-                        AmajorRun<A, R, 16>::go(D, init, e, wtab.data() + st * (D + 1), a1);
+                        const int xo = xotab[st];
+                        if (xo < 0 || xo + (int)sizeof(A) > plane) return -8;
+                        A lo0[1], lo2[1];
+                        lo0[0] = *reinterpret_cast<const A*>(rowb + xo);
+                        lo2[0] = *reinterpret_cast<const A*>(rowb + plane + xo);
+                        SelectRun<A, R, 16>::go(D, lo0, lo2, wtab.data() + ((size_t)bi * lay.passes + pi) * (D + 1) * G + g, G, a1);
                     }
                     acc[r] = a1[0];
                 }
@@ -289,6 +309,48 @@ int emu_amajor(const double* x, const double* W, long long B, int N, int K, int 
     return 0;
 }
 
+// direct kernel (every output row reads one input element): lane k of a sample evaluates x[k N / K] and its row's blocks
+template <class A, typename R>
+int emu_direct(const double* x, const double* W, long long B, int N, int K, int D, double* out, double* amps) {
+    if (D < TAN_MIN_DT || D > TAN_MAX_DT) return -4;
+    const BlockLayout lay = plan_amajor_layout(N, K, 0);
+    if (!amajor_direct_ok(N, K, lay)) return -9;
+    const int G = 1 << lay.g_k_log2;
+    const long long steps = amajor_steps(lay);
+    std::vector<CS<R>> wtab((size_t)steps * (D + 1));
+    std::vector<int> xotab(steps);
+    for (long long e = 0; e < steps; ++e)
+        fill_amajor_step<R>(e, W, N, K, D, lay.passes, lay.brows, lay.g_r_log2, lay.g_k_log2, wtab.data(), xotab.data(), (int)sizeof(A), 0);
+    int NA = 0, NB = 0, L = 0;
+    while ((1 << NA) < N) ++NA;
+    while ((1 << NB) < K) ++NB;
+    while ((1 << L) < D + 1) ++L;
+    const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    A init[4];
+    for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
+    for (long long s = 0; s < B; ++s)
+        for (int k = 0; k < K; ++k) {
+            const int nk = (int)(((long long)k * N) / K);
+            A lo0[1], lo2[1], acc[1];
+            ChebRun<A, R, 16>::go(D, init, clip_unit<R>(x[s * N + nk]), lo0[0], lo2[0]);
+            set_amp(acc[0], 0.0);
+            for (int a = 0; a < N; ++a) SelectRun<A, R, 16>::go(D, lo0, lo2, wtab.data() + (size_t)a * (D + 1) * G + k, G, acc);
+            out[s * K + k] = (double)acc[0].re / ((double)N * (D + 1));
+            if (amps) {
+                amps[2 * (s * K + k)] = (double)acc[0].re * amp_scale;
+                if constexpr (A::is_complex) amps[2 * (s * K + k) + 1] = (double)acc[0].im * amp_scale;
+                else amps[2 * (s * K + k) + 1] = 0.0;
+            }
+        }
+    return 0;
+}
+extern "C" int qkan_emu_direct_forward(int amp, const double* x, const double* W, long long B, int N, int K, int D, double* out, double* amps) {
+    if (amp == 0) return emu_direct<Cplx<double>, double>(x, W, B, N, K, D, out, amps);
+    if (amp == 1) return emu_direct<Cplx<float>, float>(x, W, B, N, K, D, out, amps);
+    if (amp == 2) return emu_direct<Real<double>, double>(x, W, B, N, K, D, out, amps);
+    return -2;
+}
+
 extern "C" int qkan_emu_amajor_forward(int amp, int min_g, int max_gk, int window_mode, const double* x, const double* W,
                                        long long B, int N, int K, int D, double* out, double* amps) {
     if (amp == 0) return emu_amajor<Cplx<double>, double>(x, W, B, N, K, D, min_g, max_gk, window_mode, out, amps);
@@ -301,6 +363,7 @@ extern "C" void qkan_emu_amajor_layout(int N, int K, int min_g, int max_gk, int*
     out4[0] = l.g_r_log2; out4[1] = l.g_k_log2; out4[2] = l.passes; out4[3] = l.brows;
     *eff = l.efficiency;
 }
+extern "C" int qkan_emu_amajor_row_amps(int n1, int G, int amp_bytes) { return amajor_row_amps(n1, G, amp_bytes); }
 extern "C" long long qkan_emu_amajor_smem(int N, int SPC, int row_bytes, int SU, int sub) { return (long long)amajor_smem_bytes(N, SPC, row_bytes, SU, sub); }
 
 // amp: 0 c128, 1 c64, 2 r64

@@ -98,6 +98,42 @@ def test_emulated_amajor_kernels_match_oracle(emu, N, K, D, min_g, max_gk):
             assert np.abs(amps[..., 1]).max() == 0.0
 
 
+@pytest.mark.parametrize("N,K,D", [(4, 4, 3), (8, 8, 1), (8, 8, 16), (16, 16, 8), (4, 8, 2), (2, 8, 5), (1, 4, 3), (1, 1, 1), (32, 32, 2), (4, 16, 7)])
+def test_emulated_direct_kernel_matches_oracle(emu, N, K, D):
+    """Direct kernel (rows that read one input element, K a multiple of N): element index, table walk, read-out."""
+    import ctypes
+    f = emu.qkan_emu_direct_forward
+    f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2
+    rng = np.random.default_rng(N + 5 * K + D)
+    B = 4
+    x = rng.uniform(-1.2, 1.2, (B, N))
+    x[1] = 0.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    spec = o.circuit_spec(N, K, D)
+    ref = o.forward_closed_form(x, W, N, K, D, "compat")
+    for amp, tol in ((0, 1e-14), (1, 1e-5), (2, 1e-14)):
+        out = np.zeros((B, K))
+        amps = np.zeros((B, K, 2))
+        assert f(amp, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data) == 0
+        assert np.abs(out - ref).max() <= tol
+        assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
+        assert np.abs(amps[..., 1]).max() == 0.0
+    assert f(0, x.ctypes.data, W.ctypes.data, B, 3, 4, D, out.ctypes.data, amps.ctypes.data) == -9      # K not a multiple of N
+
+
+def test_amajor_row_strides_spread_the_lanes(emu):
+    """amajor_row_amps: the lanes of one shared-memory phase (128 bytes) - P / G sample rows x G consecutive amplitudes of a
+    plane - land on different slots for the small power-of-two groups; rows hold both planes."""
+    for n1, G in ((5, 4), (9, 8), (17, 16), (6, 4), (4, 2), (13, 8), (3, 1), (800, 16)):
+        for ab in (16, 8):
+            P = 128 // ab
+            rs = emu.qkan_emu_amajor_row_amps(n1, G, ab)
+            assert rs >= 2 * n1
+            if G < P and n1 <= 2 * P and G <= n1:
+                slots = [((lane // G) * rs + lane % G) % P for lane in range(P)]
+                assert len(set(slots)) == P, (n1, G, ab, rs)
+
+
 def test_row_strides_are_bank_conflict_free(emu):
     """tan_row_words / cs_row_stride: the lanes of one shared-memory phase (128 bytes) that read the same member of G
     consecutive entries in P / G consecutive sample rows must land on different banks (G = 4, 8, 16 in FP64)."""

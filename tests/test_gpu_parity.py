@@ -278,7 +278,9 @@ def test_c_abi_direct(Q):
     # per (a, b): one evolution through CHEB (2 full passes of 8 FMA + the pruned pass, 4 MUL + 4 FMA), then SELECT on
     # each of the D + 1 degree copies (4 FMA)
     assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 1 and info.degree_factored == 1
-    assert info.flops_exec == 16 * (16 * 2 + 12 + 8 * 4) and info.fp_inst_exec == 16 * (8 * 3 + 4 * 4)
+    assert info.direct_rows == 1 and info.cheb_elements == 4
+    # CHEB once per evaluated input element (2 full passes of 8 FMA + the pruned pass, 4 MUL + 4 FMA), SELECT per block (4 FMA)
+    assert info.flops_exec == 4 * (16 * 2 + 12) + 64 * 8 and info.fp_inst_exec == 4 * 8 * 3 + 64 * 4
     assert info.flops_per_block_basis == 64 * (16 * 3 + 4)
     lib.qkan_layer_destroy(h)
     assert b.measure_fma_peak(0, True) > 5.0
@@ -333,10 +335,9 @@ def test_special_input_values(Q, N, K, D):
         assert_close(y, ref, dtype)
 
 
-@pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "1:256:3:1"}, {"QKAN_BLOCK_TUNE": "1:256:4:2"},
-                                 {"QKAN_BLOCK_TUNE": "1:256:3:2"}, {"QKAN_BLOCK_TUNE": "1:256:3:4"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"},
-                                 {"QKAN_BLOCK_TUNE": "1:128:8:1"}, {"QKAN_BLOCK_TUNE": "1:128:6:2"},
-                                 {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"}, {"QKAN_BLOCK_FORCE_WINDOW": "1"},
+@pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "1:256:3:2"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"},
+                                 {"QKAN_BLOCK_TUNE": "1:128:8:1"}, {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"},
+                                 {"QKAN_BLOCK_NO_DIRECT": "1"}, {"QKAN_BLOCK_FORCE_WINDOW": "1"},
                                  {"QKAN_BLOCK_STRIDED": "1"}, {"QKAN_BLOCK_STRIDED": "0"}, {"QKAN_BLOCK_SUB": "1"},
                                  {"QKAN_BLOCK_SUB": "2"}, {"QKAN_BLOCK_NO_WINDOW": "1"}, {"QKAN_HOST_PATH": "staged"}])
 def test_tuning_variants_agree(Q, env, monkeypatch):

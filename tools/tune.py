@@ -19,7 +19,7 @@ CONFIGS = {"c2": (4, 4, 3, 1_000_000), "c5d1": (8, 8, 1, 1_000_000), "c5d2": (8,
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c2,c5d1,c5d4,c5d16,c3")
-    ap.add_argument("--variants", default="0:0:0:0,1:256:4:1,1:256:3:1,1:256:4:2,1:256:3:2,1:256:3:4,1:256:2:4,1:128:8:1,1:128:6:2",
+    ap.add_argument("--variants", default="0:0:0:0,1:256:4:1,1:256:3:2,1:256:2:4,1:128:8:1",
                     help="QKAN_BLOCK_TUNE values U:NT:MINB:SU (0 = planner default); only built combinations resolve")
     ap.add_argument("--dtype", default="complex128")
     ap.add_argument("--prep", default="analytic")

@@ -260,8 +260,8 @@ def run_c5_sweep(a, torch, dist, dev, world, rank, local, flush, timed):
     out = {"workload": f"QKANLayer N=8 K=8 max_degree=1..16, {total} synthetic uniform(-1,1) inputs in total over {world} GPU(s), {a.dtype}",
            "scaling": "strong", "samples_total": total, "samples_per_rank": Bl, "steps": a.sweep_steps, "fp_peak_tflops": peak,
            "ingress_bound_ms": ((world - 1) / world * total * K * 8 / link * 1e3) if world > 1 else None, "degrees": {}}
-    full_buf = torch.empty((total, K), dtype=torch.float64, device=dev) if world > 1 else None
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    fused = {}                                                # one fused-gather wrapper per path (its symmetric buffers) serves every degree
     sizes_equal = total % world == 0
     for D in range(lo_d, hi_d + 1):
         W = torch.rand((D + 1, N * K), dtype=torch.float64, generator=torch.Generator().manual_seed(1)) * 2 - 1
@@ -295,24 +295,28 @@ def run_c5_sweep(a, torch, dist, dev, world, rank, local, flush, timed):
                 return nchunk
             g_ms, _, _, _ = timed(step_gather, a.sweep_steps, 2)
             rec["nccl_gather"] = {"samples_per_s": total * a.sweep_steps / (g_ms * 1e-3), "ms_per_step": g_ms / a.sweep_steps}
-            try:
-                from qkan_implementation_b200 import FusedGatherQKANLayer
-                fused = FusedGatherQKANLayer(layer, multicast=True)
-                fy = [None]
+            ref_list = [torch.empty_like(y[0]) for _ in range(world)]
+            dist.all_gather(ref_list, y[0])
+            ref_full = torch.cat(ref_list, dim=0)
+            for name, use_mc in (("fused_gather_multicast", True), ("fused_gather_peer_stores", False)):
+                try:
+                    from qkan_implementation_b200 import FusedGatherQKANLayer
+                    if fused.get(use_mc) is None:
+                        fused[use_mc] = FusedGatherQKANLayer(layer, multicast=use_mc)
+                    fg = fused[use_mc]
+                    fg.layer = layer
+                    fy = [None]
 
-                def step_fused():
-                    fy[0] = fused.forward(xd, Wl, total)
-                    return 1
-                f_ms, _, _, _ = timed(step_fused, a.sweep_steps, 2)
-                ref_list = [torch.empty_like(y[0]) for _ in range(world)]
-                dist.all_gather(ref_list, y[0])
-                same = bool(torch.equal(fy[0], torch.cat(ref_list, dim=0)))
-                rec["fused_gather"] = {"samples_per_s": total * a.sweep_steps / (f_ms * 1e-3), "ms_per_step": f_ms / a.sweep_steps,
-                                       "path": fused.last_path, "bitwise_equal_to_sharded": same,
-                                       "ingress_bound_frac": out["ingress_bound_ms"] / (f_ms / a.sweep_steps)}
-                del fused
-            except Exception as e:      # noqa: BLE001  (report, do not hide)
-                rec["fused_gather"] = {"error": f"{type(e).__name__}: {e}"}
+                    def step_fused():
+                        fy[0] = fg.forward(xd, Wl, total)
+                        return 1
+                    f_ms, _, _, _ = timed(step_fused, a.sweep_steps, 2)
+                    rec[name] = {"samples_per_s": total * a.sweep_steps / (f_ms * 1e-3), "ms_per_step": f_ms / a.sweep_steps,
+                                 "path": fg.last_path, "bitwise_equal_to_sharded": bool(torch.equal(fy[0], ref_full)),
+                                 "ingress_bound_frac": out["ingress_bound_ms"] / (f_ms / a.sweep_steps)}
+                except Exception as e:      # noqa: BLE001  (report, do not hide)
+                    rec[name] = {"error": f"{type(e).__name__}: {e}"}
+            del ref_list, ref_full
         if rank == 0:
             sps = rec["sharded"]["samples_per_s"]
             rec["sharded"]["frac"] = info["flops_exec"] * sps / 1e12 / (peak * world)

@@ -93,6 +93,13 @@ int qkan_layer_out_of_range(qkan_layer* layer, uint64_t* count);
 int qkan_layer_diagonals(qkan_layer* layer, const double* x, int64_t B, double* cheb, double* weighted,
                          double* lcu, void* cuda_stream);
 
+/* The same three stages read out of the SIMULATED circuit (QKANLayer.py:52-66): the post-selected (f_x, f_w) = (0, 0)
+ * block amplitudes after the CHEB sequence (cheb), after the SELECT rotation of every degree term (weighted) and after
+ * the degree sum (lcu), produced by the evolution functions the forward kernels run - scaled rotations + SELECT for
+ * compat mode with 1 <= D <= 16, plain (cos, sin) rotations otherwise - instead of the closed form cos(D arccos x). */
+int qkan_layer_stage_snapshots(qkan_layer* layer, const double* x, int64_t B, double* cheb, double* weighted,
+                               double* lcu, void* cuda_stream);
+
 /* Description of the kernel the layer resolved to, and its work per sample. */
 typedef struct {
     int engine;                 /* 0 = block engine (prep = analytic, default); 1 = staged full-statevector

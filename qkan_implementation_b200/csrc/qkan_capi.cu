@@ -54,6 +54,28 @@ int clog2(int n) {
 
 constexpr int MAX_CHUNKS = 64;
 
+// every entry point runs on the layer's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;               // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                            \
+    DeviceGuard _guard(dev);                                      \
+    if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice")
+
+__global__ void qkan_check_weights_kernel(const double* W, long long n, unsigned long long* bad) {
+    unsigned cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        if (!(fabs(W[i]) <= 1.0)) ++cnt;
+    if (cnt) atomicAdd(bad, (unsigned long long)cnt);
+}
+
 }  // namespace
 
 struct qkan_layer {
@@ -237,7 +259,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
             return fail(QKAN_ERR_UNSUPPORTED, buf);
         }
     }
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     qkan_layer* l = new qkan_layer();
     l->N = N; l->K = K; l->D = max_degree; l->NA = NA; l->NB = NB; l->L = L;
     l->dtype = dtype; l->mode = mode; l->prep = prep; l->device = device;
@@ -276,7 +298,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
 
 extern "C" void qkan_layer_destroy(qkan_layer* l) {
     if (!l) return;
-    cudaSetDevice(l->device);
+    DeviceGuard guard(l->device);
     cudaFree(l->wtab); cudaFree(l->xidx); cudaFree(l->counters); cudaFree(l->W_dev);
     cudaFree(l->d_x); cudaFree(l->d_out); cudaFree(l->d_amps);
     if (l->s_in) cudaStreamDestroy(l->s_in);
@@ -297,8 +319,23 @@ extern "C" void qkan_layer_destroy(qkan_layer* l) {
 extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_device, int validate, void* cuda_stream) {
     if (!l || !W) return fail(QKAN_ERR_BAD_SHAPE, "null layer or weights");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     const size_t nw = (size_t)(l->D + 1) * l->N * l->K;
+    if (validate) {
+        // |w| <= 1 (MulStep.py:36-37) is checked BEFORE anything is overwritten: a rejected matrix leaves the previous
+        // weights and tables in place, like the reference's set_weights, which raises before it assigns
+        unsigned long long bad = 0;
+        if (on_device) {
+            CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
+            qkan_check_weights_kernel<<<64, 256, 0, stream>>>(W, (long long)nw, l->counters + 1);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(&bad, l->counters + 1, sizeof bad, cudaMemcpyDeviceToHost, stream));
+            CU(cudaStreamSynchronize(stream));
+        } else {
+            for (size_t i = 0; i < nw; ++i) bad += !(fabs(W[i]) <= 1.0);
+        }
+        if (bad) return fail(QKAN_ERR_WEIGHT_RANGE, "Weight magnitudes must be <= 1 for unitarity");   // MulStep.py:37
+    }
     if (W != l->W_dev)
         CU(cudaMemcpyAsync(l->W_dev, W, nw * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                            stream));
@@ -342,15 +379,6 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
                                                                   (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     }
     CU(cudaGetLastError());
-    if (validate) {
-        unsigned long long bad = 0;
-        CU(cudaMemcpyAsync(&bad, l->counters + 1, sizeof bad, cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        if (bad) {
-            l->weights_set = false;
-            return fail(QKAN_ERR_WEIGHT_RANGE, "Weight magnitudes must be <= 1 for unitarity");   // MulStep.py:37
-        }
-    }
     if (!l->ev_w) CU(cudaEventCreateWithFlags(&l->ev_w, cudaEventDisableTiming));
     CU(cudaEventRecord(l->ev_w, stream));
     l->weights_set = true;
@@ -400,7 +428,7 @@ extern "C" int qkan_layer_forward(qkan_layer* l, const double* x, int64_t B, dou
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
     if (B == 0) return QKAN_OK;
     if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     return launch_on(l, x, B, out, amps, (cudaStream_t)cuda_stream);
 }
 
@@ -442,7 +470,7 @@ extern "C" int qkan_layer_forward_peers(qkan_layer* l, const double* x, int64_t 
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
     if (B == 0) return QKAN_OK;
     if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     return launch_on(l, x, B, (double*)out_ptrs[0], nullptr, (cudaStream_t)cuda_stream, out_ptrs, n_ptrs, row_offset);
 }
 
@@ -455,7 +483,7 @@ extern "C" int qkan_layer_forward_multicast(qkan_layer* l, const double* x, int6
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
     if (B == 0) return QKAN_OK;
     if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     return launch_on(l, x, B, nullptr, nullptr, (cudaStream_t)cuda_stream, nullptr, 0, row_offset, mc_out);
 }
 
@@ -465,7 +493,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
     if (B == 0) return QKAN_OK;
     if (!x || !out) return fail(QKAN_ERR_BAD_SHAPE, "null x / out");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     // Pinned (page-locked, device-mapped) host buffers can be used by the kernel directly: it streams x from host memory
     // itself and / or stores every result straight into the host buffer, so that side needs no staging copy and crosses
     // PCIe concurrently with the arithmetic.  Each side is either "direct" (kernel access) or "copy" (chunked
@@ -600,7 +628,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
 
 extern "C" int qkan_layer_out_of_range(qkan_layer* l, uint64_t* count) {
     if (!l || !count) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     CU(cudaDeviceSynchronize());
     unsigned long long v = 0;
     CU(cudaMemcpy(&v, l->counters, sizeof v, cudaMemcpyDeviceToHost));
@@ -718,12 +746,90 @@ extern "C" int qkan_layer_diagonals(qkan_layer* l, const double* x, int64_t B, d
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "diagonals called before set_weights");
     if (B == 0) return QKAN_OK;
     if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
-    CU(cudaSetDevice(l->device));
+    ON_DEVICE(l->device);
     const long long total = (long long)B * l->N * l->K;
     const unsigned nt = 256;
     const unsigned nb = (unsigned)((total + nt - 1) / nt);
     qkan_diagonals_kernel<<<nb, nt, 0, (cudaStream_t)cuda_stream>>>(x, l->W_dev, B, l->N, l->K, l->D, l->mode, cheb,
                                                                     weighted, lcu);
+    CU(cudaGetLastError());
+    return QKAN_OK;
+}
+
+// Stage snapshots of the SIMULATED circuit (debug / verbose path): the post-selected block amplitudes after the CHEB
+// sequence, after SELECT and after the degree sum, read out of the same evolution functions the forward kernels run
+// (cheb_element + the SELECT rotation of qkan_amajor.cuh for compat mode, 1 <= D <= 16; evolve_blocks of
+// qkan_block.cuh otherwise) - not the closed form cos(D arccos x) of qkan_diagonals_kernel, which they are tested
+// against.  One thread per (sample, i), i = a + N b (the reference's diagonal index, QKANLayer.py:131-132).
+template <int DT>
+__device__ __forceinline__ void snapshot_block(const Cplx<double> (&init)[4], double xc, const double* W, long long NK, int i, int D,
+                                               int mode, double* cheb_out, double* wtd_out, long long wtd_stride, double* lcu_out) {
+    typedef Cplx<double> A;
+    double acc = 0.0;
+    if constexpr (DT > 0) {
+        A lo0, lo2;
+        cheb_element<A, double, DT>(init, xc, lo0, lo2);      // f_x = 0 amplitudes of the block after CHEB
+        if (cheb_out) *cheb_out = lo0.re;
+        for (int d = 0; d <= D; ++d) {
+            const double w = W[(long long)d * NK + i];
+            const double sw = sqrt((1.0 - w) * (1.0 + w));
+            const double z = fma(w, lo0.re, -(sw * lo2.re));  // (f_x, f_w) = (0, 0) amplitude after SELECT
+            if (wtd_out) wtd_out[(long long)d * wtd_stride] = z;
+            acc += z / (double)(D + 1);                       // LCUStep.py:36 (sequential, degree order)
+        }
+    } else {
+        const double cx[1] = {xc}, sx[1] = {sqrt((1.0 - xc) * (1.0 + xc))};
+        const double one[1] = {1.0}, zero[1] = {0.0};
+        const int dmax[1] = {D};
+        if (cheb_out) *cheb_out = evolve_blocks<A, double, 1, 1, 0>(init, cx, sx, one, zero, dmax, D).re;   // every application on
+        for (int d = 0; d <= D; ++d) {
+            const double w = W[(long long)d * NK + i];
+            const double cw[1] = {w}, sw[1] = {sqrt((1.0 - w) * (1.0 + w))};
+            const int deg[1] = {mode == 1 ? d : D};           // paper mode: term d gets d applications
+            const double z = evolve_blocks<A, double, 1, 1, 0>(init, cx, sx, cw, sw, deg, D).re;
+            if (wtd_out) wtd_out[(long long)d * wtd_stride] = z;
+            acc += z / (double)(D + 1);
+        }
+    }
+    if (lcu_out) *lcu_out = acc;
+}
+
+__global__ void qkan_stage_snapshot_kernel(const double* x, const double* W, long long B, int N, int K, int D, int mode,
+                                           double* cheb, double* weighted, double* lcu) {
+    const long long NK = (long long)N * K;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= B * NK) return;
+    const long long s = gid / NK;
+    const int i = (int)(gid - s * NK);
+    const double xc = clip_unit<double>(x[s * N + i / K]);           // ChebyshevStep.py:52,64
+    Cplx<double> init[4];
+    for (int q = 0; q < 4; ++q) { init[q].re = q == 0 ? 1.0 : 0.0; init[q].im = 0.0; }   // PREPARE'd block state, un-normalised
+    double* c = cheb ? cheb + gid : nullptr;
+    double* w = weighted ? weighted + s * (D + 1) * NK + i : nullptr;
+    double* l = lcu ? lcu + gid : nullptr;
+    const bool tan = mode == 0 && D >= TAN_MIN_DT && D <= TAN_MAX_DT;
+    switch (tan ? D : 0) {
+#define SNAP_CASE(DT) case DT: snapshot_block<DT>(init, xc, W, NK, i, D, mode, c, w, NK, l); break;
+        SNAP_CASE(1) SNAP_CASE(2) SNAP_CASE(3) SNAP_CASE(4) SNAP_CASE(5) SNAP_CASE(6) SNAP_CASE(7) SNAP_CASE(8)
+        SNAP_CASE(9) SNAP_CASE(10) SNAP_CASE(11) SNAP_CASE(12) SNAP_CASE(13) SNAP_CASE(14) SNAP_CASE(15) SNAP_CASE(16)
+#undef SNAP_CASE
+        default: snapshot_block<0>(init, xc, W, NK, i, D, mode, c, w, NK, l); break;
+    }
+}
+
+extern "C" int qkan_layer_stage_snapshots(qkan_layer* l, const double* x, int64_t B, double* cheb, double* weighted,
+                                          double* lcu, void* cuda_stream) {
+    if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
+    if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
+    if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "stage snapshots called before set_weights");
+    if (B == 0) return QKAN_OK;
+    if (!x) return fail(QKAN_ERR_BAD_SHAPE, "null x");
+    ON_DEVICE(l->device);
+    const long long total = (long long)B * l->N * l->K;
+    const unsigned nt = 128;
+    const unsigned nb = (unsigned)((total + nt - 1) / nt);
+    qkan_stage_snapshot_kernel<<<nb, nt, 0, (cudaStream_t)cuda_stream>>>(x, l->W_dev, B, l->N, l->K, l->D, l->mode, cheb,
+                                                                         weighted, lcu);
     CU(cudaGetLastError());
     return QKAN_OK;
 }
@@ -767,7 +873,7 @@ template <typename R> __global__ void __launch_bounds__(256) fma_peak_kernel(R* 
 
 extern "C" int qkan_measure_fma_peak(int device, int fp64, double* tflops) {
     if (!tflops) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     const int grid = prop.multiProcessorCount * 8, nt = 256, iters = fp64 ? 8192 : 16384;

@@ -515,6 +515,9 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* sink, int iters,
 
 extern "C" int qkan_measure_dmma_peak(int device, double* tflops) {
     if (!tflops) return fail(QKAN_ERR_BAD_SHAPE, "null argument");
+    int prev_device = -1;
+    cudaGetDevice(&prev_device);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_device == device ? -1 : prev_device};
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     int sms = 148;

@@ -53,22 +53,33 @@ class FusedGatherQKANLayer:
     mappings), so there is no separate collective and the transfer overlaps the arithmetic.  After
     ``forward`` (which ends with a symmetric-memory barrier) every rank holds the full ``[B, K]``.
 
-    One process per GPU, NCCL process group initialised, CUDA ``QKANLayer`` with ``prep="analytic"``."""
+    One process per GPU, NCCL process group initialised, CUDA ``QKANLayer`` with ``prep="analytic"``.
+
+    The result lives in symmetric memory that the peers write into.  Two buffers per shape alternate between
+    calls, and every call ends with a barrier (``barrier=True``), so a rank that is already in call i+1 stores into
+    the other buffer while a slower peer may still be reading the result of call i; the tensor returned by call i is
+    overwritten by call i+2.  With ``barrier=False`` nothing orders the ranks: the caller must synchronise them
+    (e.g. ``dist.barrier()``) before reading the result AND before the next-but-one call."""
 
     def __init__(self, layer, group=None, multicast: bool = True):
         self.layer = layer
         self.group = group if group is not None else dist.group.WORLD
         self.multicast = multicast          # use the NVSwitch multicast mapping when the fabric offers one
         self._bufs = {}
+        self._calls = {}
 
     def _buffer(self, B: int, K: int, device):
         import torch.distributed._symmetric_memory as symm_mem
         key = (B, K)
         if key not in self._bufs:
-            t = symm_mem.empty((B, K), dtype=torch.float64, device=device)
-            hdl = symm_mem.rendezvous(t, self.group)
-            self._bufs[key] = (t, hdl)
-        return self._bufs[key]
+            pair = []
+            for _ in range(2):
+                t = symm_mem.empty((B, K), dtype=torch.float64, device=device)
+                pair.append((t, symm_mem.rendezvous(t, self.group)))
+            self._bufs[key] = pair
+            self._calls[key] = 0
+        self._calls[key] += 1
+        return self._bufs[key][self._calls[key] & 1]
 
     def forward(self, x_local: torch.Tensor, weights, B_total: int, barrier: bool = True) -> torch.Tensor:
         """x_local: this rank's contiguous slice (shard_bounds) as a CUDA tensor [B_local, N]."""

@@ -79,6 +79,16 @@ class FableCircuit:
     def size(self) -> int:
         return len(self.gates)
 
+    def depth(self) -> int:
+        """Circuit depth as qiskit.QuantumCircuit.depth() counts it: the longest chain of gates that share a qubit."""
+        level = [0] * self.num_qubits
+        for kind, q0, q1 in self.gates:
+            qs = (q0, q1) if kind in (CX, SWAP) else (q0,)
+            d = 1 + max(level[q] for q in qs)
+            for q in qs:
+                level[q] = d
+        return max(level) if level else 0
+
     # -------------------------------------------------------------- GPU evaluation
     def columns(self, basis_states) -> np.ndarray:
         """Evolve |j> for every j in ``basis_states`` on the GPU; returns complex128 [len, 2^num_qubits]."""

@@ -82,9 +82,11 @@ class _Engine:
         self._uploaded_version = version
 
     def upload_device_weights(self, W, validate: bool = True):
+        # a rejected matrix (|w| > 1) leaves the previous tables in place; whatever happens, the host-side version
+        # stamp no longer describes the device tables, so the next host upload is not skipped
+        self._uploaded_version = -2
         _b.check(_b.lib().qkan_layer_set_weights(self.handle(), W.data_ptr(), 1, 1 if validate else 0,
                                                  self._stream_ptr()))
-        self._uploaded_version = -2
 
     def _stream_ptr(self):
         if torch is not None and torch.cuda.is_available():
@@ -105,7 +107,15 @@ class _Engine:
                                                   amps.ctypes.data if want_amps else None))
         return out, amps
 
+    def _check_device(self, t):
+        """The engine owns tables on ONE device; tensors of another device would be handed to its kernel as raw pointers."""
+        self.handle()
+        if t.device.index != self.device:
+            raise ValueError(f"tensor on cuda:{t.device.index} but this layer's engine lives on cuda:{self.device}; "
+                             "create the layer with device=... or move the tensor")
+
     def forward_device(self, x, want_amps: bool):
+        self._check_device(x)
         B = x.shape[0]
         out = torch.empty((B, self.K), dtype=torch.float64, device=x.device)
         amps = None
@@ -126,8 +136,11 @@ class _Engine:
         _b.check(_b.lib().qkan_layer_info(self.handle(), ctypes.byref(ki)))
         return ki.as_dict()
 
-    def diagonals(self, x: np.ndarray):
-        """cheb [B,NK], weighted [B,D+1,NK], lcu [B,NK] computed on the GPU."""
+    def diagonals(self, x: np.ndarray, source: str = "closed_form"):
+        """cheb [B,NK], weighted [B,D+1,NK], lcu [B,NK] computed on the GPU.  source="circuit": stage snapshots of the
+        simulated circuit (post-selected block amplitudes); "closed_form": cos(D arccos x) like the reference."""
+        if source not in ("closed_form", "circuit"):
+            raise ValueError("source must be 'closed_form' or 'circuit'")
         if torch is None or not torch.cuda.is_available():
             raise RuntimeError("qkan_implementation_b200 needs a CUDA device (no CPU fallback)")
         dev = torch.device("cuda", self.device if self.device is not None else torch.cuda.current_device())
@@ -136,8 +149,8 @@ class _Engine:
         cheb = torch.empty((B, NK), dtype=torch.float64, device=dev)
         wtd = torch.empty((B, self.D + 1, NK), dtype=torch.float64, device=dev)
         lcu = torch.empty((B, NK), dtype=torch.float64, device=dev)
-        _b.check(_b.lib().qkan_layer_diagonals(self.handle(), xd.data_ptr(), B, cheb.data_ptr(), wtd.data_ptr(),
-                                               lcu.data_ptr(), self._stream_ptr()))
+        fn = _b.lib().qkan_layer_stage_snapshots if source == "circuit" else _b.lib().qkan_layer_diagonals
+        _b.check(fn(self.handle(), xd.data_ptr(), B, cheb.data_ptr(), wtd.data_ptr(), lcu.data_ptr(), self._stream_ptr()))
         return cheb.cpu().numpy(), wtd.cpu().numpy(), lcu.cpu().numpy()
 
 
@@ -291,10 +304,16 @@ class QKANLayer:
                 raise ValueError(f"Degree must be between 0 and {self.max_degree}")
             if weights.shape[1] != self.N * self.K:
                 raise ValueError(f"Expected {self.N * self.K} weights, got {weights.shape[1]}")
+            self._engine._check_device(weights)
+            # the same tensor, unmodified since its last upload: tables, host mirror and validation are all current
+            stamp = (weights.data_ptr(), weights._version, tuple(weights.shape), weights.dtype)
+            if getattr(self, "_device_stamp", None) == stamp and self._engine._uploaded_version == self.mul_step._version:
+                return
             if weights.shape[0] != self.max_degree + 1 or weights.dtype != torch.float64 or not weights.is_contiguous():
                 full = torch.as_tensor(self.mul_step._weights, device=weights.device).clone()
                 full[: weights.shape[0]] = weights.to(torch.float64)
                 weights = full
+            self._device_stamp = None
             try:
                 self._engine.upload_device_weights(weights, validate=True)
             except _b.QkanError as e:
@@ -305,6 +324,7 @@ class QKANLayer:
             self.mul_step._weights[:] = weights.detach().cpu().numpy()
             self.mul_step._version += 1
             self._engine._uploaded_version = self.mul_step._version
+            self._device_stamp = stamp
             return
         for degree, w in enumerate(weights):
             if check_len and len(w) != self.N * self.K:
@@ -371,8 +391,10 @@ class QKANLayer:
         return self._engine.info()
 
     # ------------------------------------------------------ intermediate matrices
-    def get_intermediate_matrices(self, x, weights) -> dict:
-        """QKANLayer.py:30-75: dense intermediates of one sample, diagonals computed on the GPU."""
+    def get_intermediate_matrices(self, x, weights, source: str = "circuit") -> dict:
+        """QKANLayer.py:30-75: dense intermediates of one sample.  The diagonals are stage snapshots of the simulated
+        circuit (source="circuit": the post-selected block amplitudes after CHEB, after SELECT and after the degree
+        sum) or the reference's closed form evaluated on the GPU (source="closed_form")."""
         if len(x) != self.N:
             raise ValueError(f"Expected input dimension {self.N}, got {len(x)}")
         if len(weights) != self.max_degree + 1:
@@ -382,7 +404,7 @@ class QKANLayer:
         violations = x[~(-1 - EPS_RANGE <= x) | ~(x <= 1 + EPS_RANGE)]
         if len(violations) > 0:
             print(f"Values outside [-1,1] range: {violations[:5]}")
-        cheb, wtd, lcu = self._engine.diagonals(x[None, :])
+        cheb, wtd, lcu = self._engine.diagonals(x[None, :], source)
         D = self.max_degree
         results = {"input": x}
         results["cheb"] = {d: np.diag(cheb[0]) for d in range(D + 1)}          # degree quirk, :54-57
@@ -393,12 +415,12 @@ class QKANLayer:
         results["final"] = out
         return results
 
-    def get_intermediate_diagonals(self, x) -> dict:
+    def get_intermediate_diagonals(self, x, source: str = "circuit") -> dict:
         """Batched variant: x [B, N] -> dict of diagonals cheb [B,NK], weighted [B,D+1,NK], lcu [B,NK],
-        reshaped [B,N,K], final [B,K] (weights as last set)."""
+        reshaped [B,N,K], final [B,K] (weights as last set); `source` as in get_intermediate_matrices."""
         x = np.atleast_2d(np.asarray(x, dtype=np.float64))
         self._engine.upload_host_weights(self.mul_step._weights, self.mul_step._version)
-        cheb, wtd, lcu = self._engine.diagonals(x)
+        cheb, wtd, lcu = self._engine.diagonals(x, source)
         reshaped = lcu.reshape(-1, self.K, self.N).transpose(0, 2, 1)
         final = self._engine.forward_host(np.ascontiguousarray(x), False)[0]
         return {"cheb": cheb, "weighted": wtd, "lcu": lcu, "reshaped": reshaped, "final": final}

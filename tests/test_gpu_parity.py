@@ -91,6 +91,34 @@ def test_intermediate_matrices_and_verbose(Q, capsys):
     assert d["weighted"].shape == (2, 4, 16) and np.abs(d["lcu"][0] - g["lcu_diag"]).max() <= 1e-15
 
 
+@pytest.mark.parametrize("N,K,D,mode", [(4, 4, 3, "compat"), (8, 8, 1, "compat"), (8, 8, 16, "compat"), (5, 3, 7, "compat"), (16, 16, 8, "compat"),
+                                        (4, 4, 20, "compat"), (4, 4, 0, "compat"), (4, 4, 3, "paper"), (6, 5, 9, "paper")])
+def test_stage_snapshots_of_the_circuit(Q, N, K, D, mode):
+    """QKANLayer.py:52-66 from the SIMULATED circuit: the post-selected block amplitudes after CHEB / SELECT / the degree
+    sum (qkan_layer_stage_snapshots) equal the closed form evaluated classically (qkan_layer_diagonals, and NumPy here),
+    and summing the lcu snapshot like QKANLayer.py:131-133 reproduces forward()."""
+    rng = np.random.default_rng(N * 100 + K * 10 + D)
+    B = 19
+    x = rng.uniform(-1.1, 1.1, (B, N))
+    x[0] = 0.0
+    x[1, 0], x[2, 0] = 1.0, -1.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    layer = Q.QKANLayer(N, K, D, mode=mode)
+    layer._set_weights(list(W))
+    snap = layer.get_intermediate_diagonals(x, source="circuit")
+    ref = layer.get_intermediate_diagonals(x, source="closed_form")
+    th = np.arccos(np.clip(x, -1, 1))[:, np.arange(N * K) // K]                 # ChebyshevStep.py:52,64
+    cheb_np = np.cos(D * th)
+    assert np.abs(snap["cheb"] - cheb_np).max() <= 5e-14 and np.abs(ref["cheb"] - cheb_np).max() <= 5e-14
+    for d in range(D + 1):
+        c = cheb_np if mode == "compat" else np.cos(d * th)
+        assert np.abs(snap["weighted"][:, d] - c * W[d]).max() <= 5e-14        # MulStep.py:72
+    assert np.abs(snap["lcu"] - ref["lcu"]).max() <= 5e-14
+    out = snap["lcu"].reshape(B, K, N).sum(axis=2) / N                          # QKANLayer.py:131-133
+    assert np.abs(out - layer.forward(x, list(W))).max() <= 1e-14
+    assert np.abs(snap["final"] - o.forward_closed_form(x, W, N, K, D, mode)).max() <= 1e-13
+
+
 def test_step_api_known_answers(Q):
     k = np.load(f"{GOLDEN}/kat_steps.npz")
     assert abs(Q.ChebyshevStep(1).apply_chebyshev(0.5) - 0.5) < 1e-15           # ChebyshevStep.py:73
@@ -361,6 +389,46 @@ def test_tuning_variants_agree(Q, env, monkeypatch):
         op = torch.empty((B, K), dtype=torch.float64).pin_memory()
         layer.forward(xp.numpy(), W, out=op.numpy(), check_range=False)          # pinned: zero-copy (or staged by env)
         assert_close(op.numpy(), ref)
+
+
+def test_rejected_device_weights_leave_the_layer_usable(Q):
+    """|w| > 1 in a CUDA weight tensor raises like MulStep.set_weights (MulStep.py:36-37) BEFORE anything is overwritten:
+    the next forward with the previous (host) weights gives the previous result."""
+    rng = np.random.default_rng(3)
+    N, K, D = 4, 4, 3
+    x = rng.uniform(-1, 1, (33, N))
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    layer = Q.QKANLayer(N, K, D)
+    ref = layer.forward(x, list(W))
+    bad = torch.from_numpy(W * 1.5).cuda()
+    with pytest.raises(ValueError, match="Weight magnitudes"):
+        layer.forward(torch.from_numpy(x).cuda(), bad)
+    assert np.array_equal(layer.mul_step._weights, W)                          # host mirror untouched
+    assert np.array_equal(layer.forward(x, list(W)), ref)                      # and the device tables still serve it
+    good = torch.from_numpy(W * 0.5).cuda()
+    y = layer.forward(torch.from_numpy(x).cuda(), good)
+    assert_close(y.cpu().numpy(), o.forward_closed_form(x, W * 0.5, N, K, D))
+    assert torch.equal(layer.forward(torch.from_numpy(x).cuda(), good), y)     # same tensor again: upload skipped
+    good.mul_(0.5)                                                             # modified in place: uploaded again
+    assert_close(layer.forward(torch.from_numpy(x).cuda(), good).cpu().numpy(), o.forward_closed_form(x, W * 0.25, N, K, D))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_engine_device_is_checked_and_current_device_kept(Q):
+    """The engine's tables live on one device: tensors of another device are refused, and no call changes the caller's
+    current device."""
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-1, 1, (17, 4))
+    W = rng.uniform(-1, 1, (4, 16))
+    torch.cuda.set_device(0)
+    layer = Q.QKANLayer(4, 4, 3, device=1)
+    y = layer.forward(torch.from_numpy(x).to("cuda:1"), list(W))
+    assert y.device.index == 1 and torch.cuda.current_device() == 0
+    assert_close(y.cpu().numpy(), o.forward_closed_form(x, W, 4, 4, 3))
+    assert_close(layer.forward(x, list(W)), o.forward_closed_form(x, W, 4, 4, 3))   # host buffers
+    assert torch.cuda.current_device() == 0
+    with pytest.raises(ValueError, match="engine lives on cuda:1"):
+        layer.forward(torch.from_numpy(x).to("cuda:0"), list(W))
 
 
 @pytest.mark.parametrize("D", [0, 1, 3, 4, 16, 17])

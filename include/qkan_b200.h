@@ -122,6 +122,9 @@ typedef struct {
                                    mode, 1 <= D <= 16); 0: plain (cos, sin) rotations                         */
     int input_window;           /* > 0: window kernel (wide input rows) - rotation entries are built per row step
                                    from this many inputs instead of once per sample from all N                 */
+    int element_owner;          /* 1: element-owner kernel (wide input rows) - the lanes of a row own its input elements: each
+                                   loads x[n], runs CHEB in registers and applies SELECT to the K (D+1) blocks the element
+                                   feeds; no shared memory, samples_per_lane samples share every SELECT entry        */
     int degree_factored;        /* 1: a-major kernels - blocks that share a CHEB evolution share its arithmetic: the D + 1
                                    degree copies of an (a, b) block (the state is (block) (x) |+>_deg until SELECT) and
                                    the blocks that read the same input element x[(a + N b) / K] (repeated entries of

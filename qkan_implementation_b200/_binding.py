@@ -33,7 +33,7 @@ class KernelInfo(ctypes.Structure):
                  "blocks", "unroll", "samples_per_lane", "lanes_per_sample", "lanes_per_row", "rows_in_parallel", "passes", "row_steps",
                  "tile_qubits", "tile_na", "tile_nb", "local_qubits", "stages", "sectors_total", "sectors_run",
                  "threads_per_cta", "min_ctas_per_sm", "samples_per_cta", "grid", "smem_bytes",
-                 "passes_survey", "passes_exec", "scaled_rotations", "input_window", "degree_factored", "cheb_elements", "direct_rows")] + \
+                 "passes_survey", "passes_exec", "scaled_rotations", "input_window", "element_owner", "degree_factored", "cheb_elements", "direct_rows")] + \
                [(n, ctypes.c_double) for n in
                 ("flops_survey", "flops_per_block_basis", "flops_exec", "fp_inst_exec", "layout_efficiency", "io_bytes")]
 

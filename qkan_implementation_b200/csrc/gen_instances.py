@@ -107,7 +107,13 @@ DIRECT = {
     (4, 256): [(2, 1)],
     (2, 256): [(3, 0)],      # tuning variant (complex128 only)
 }
-WINDOW_CTAS = ((256, 3, 1),)   # (NT, MINB, is_default) of the window kernels (wide input rows); MINB 4 measured slower on N784 K10 D5
+# element-owner kernels (wide input rows): (SU, NT) -> [(MINB, is_default)]
+ELEM = {
+    (4, 256): [(2, 1)],
+    (2, 256): [(3, 1)],
+    (1, 256): [(4, 1)],
+}
+WINDOW_CTAS = ()   # the window kernel of round 1 is superseded by the element-owner kernel
 
 
 def amajor_instances():
@@ -117,6 +123,18 @@ def amajor_instances():
             for (SU, NT), variants in AMAJOR.items():
                 for (minb, dflt) in variants:
                     if not dflt and amp != "c128":
+                        continue
+                    out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
+    return out
+
+
+def elem_instances():
+    out = []   # (group, amp, SU, NT, MINB, DT, is_default)
+    for amp in ("c128", "c64", "r64"):
+        for dt in range(1, DT_MAX + 1):
+            for (SU, NT), variants in ELEM.items():
+                for (minb, dflt) in variants:
+                    if SU != 4 and amp != "c128":
                         continue
                     out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
     return out
@@ -168,6 +186,9 @@ def main():
     dgroups = {}
     for it in direct_instances():
         dgroups.setdefault(it[0], []).append(it)
+    egroups = {}
+    for it in elem_instances():
+        egroups.setdefault(it[0], []).append(it)
     wgroups = {}
     for it in window_instances():
         wgroups.setdefault(it[0], []).append(it)
@@ -214,6 +235,9 @@ def main():
         for (_, amp, SU, NT, MINB, DT, dflt) in dgroups.get(g, []):
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_direct_info<{A}, {R}, {SU}, {NT}, {MINB}, {DT}>({dflt}));\n")
+        for (_, amp, SU, NT, MINB, DT, dflt) in egroups.get(g, []):
+            A, R, _sz = AMPS[amp]
+            fh.write(f"    reg.push_back(make_elem_info<{A}, {R}, {SU}, {NT}, {MINB}, {DT}>({dflt}));\n")
         for (_, amp, NT, MINB, DT, dflt) in wgroups.get(g, []):
             A, R, _sz = AMPS[amp]
             fh.write(f"    reg.push_back(make_amajor_window_info<{A}, {R}, {NT}, {MINB}, {DT}>({dflt}));\n")

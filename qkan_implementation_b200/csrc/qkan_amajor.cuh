@@ -137,7 +137,6 @@ inline size_t amajor_smem_bytes(int N, int SPC, int row_bytes, int SU, int sub) 
     const size_t cs = ((tile + (size_t)(SU - 1) * SPC) * (size_t)row_bytes + 15) & ~(size_t)15;
     return xs + cs + 16;
 }
-inline size_t amajor_window_smem_bytes(int SPC, int row_bytes, int sub) { return (size_t)SPC * sub * row_bytes; }
 constexpr size_t AMAJOR_SMEM_CAP = 200 * 1024;
 
 // CHEB on one input element: the block state `init` through D applications of Ry(theta_x), cos(theta_x / 2) = c,
@@ -177,6 +176,92 @@ QK_HD void select_blocks(const A (&lo0)[SU], const A (&lo2)[SU], const CS<R>* __
 // direct kernel applies: one row step, one lane per row, each row reads a single input element
 inline bool amajor_direct_ok(int N, int K, const BlockLayout& lay) {
     return K % N == 0 && lay.g_r_log2 == 0 && lay.brows == 1 && lay.efficiency == 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Element-owner walk (wide input rows, e.g. N784 K10): output row b reads the inputs n_first(b) .. n_last(b),
+// n = (a + N b) / K, about N / K of them, and input n feeds the K consecutive summed indices a = n K - N b + j,
+// j < K.  Lane (k, r) of a sample owns the elements e = pi G_r + r of its row b = bi G_k + k: it loads x[n] itself,
+// runs the CHEB sequence in registers and applies SELECT to the element's K (D + 1) blocks.  Nothing is staged in
+// shared memory, so SU samples per lane cost registers only, and every SELECT entry a warp loads serves
+// (32 / G) SU samples - what keeps the L1 pipe (one 128-byte wavefront per cycle) behind the FP64 pipe.
+// Tables:   xe[(bi * passes + pi) * G + g]                       = n | (count << 30) | (live << 31 as sign: -1 = padding)
+//           we[(((bi * passes + pi) * K + j) * (D + 1) + d) * G + g] = (cos, sin)(theta_w / 2) of block (a, b, d)
+struct ElemLayout {
+    int g_r_log2, g_k_log2, passes, brows;
+    double efficiency;
+};
+QK_HD void elem_row_range(int N, int K, long long b, long long* n_first, long long* n_last) {
+    *n_first = (b * N) / K;
+    *n_last = (b * N + N - 1) / K;
+}
+inline ElemLayout plan_elem_layout(int N, int K, int min_g_log2 = 0) {
+    ElemLayout best{};
+    double best_score = -1.0;
+    long long wmax = 1;
+    for (long long b = 0; b < K; ++b) {
+        long long f, l;
+        elem_row_range(N, K, b, &f, &l);
+        if (l - f + 1 > wmax) wmax = l - f + 1;
+    }
+    // rows one after the other (G_k = 1: the most samples per warp share a table load); the lanes of a row split its
+    // elements: the widest split up to 16 lanes (16 consecutive inputs = one 128-byte line per load) that keeps the
+    // padding of the last pass below 10 % of the best split
+    double eff_max = 0.0;
+    for (int gr = 0; gr <= 5; ++gr) {
+        const long long G_r = 1ll << gr, passes = (wmax + G_r - 1) / G_r;
+        const double eff = (double)N / (double)(passes * G_r * K);      // live blocks / issued block slots of a row
+        if (eff > eff_max) eff_max = eff;
+    }
+    int force_gr = -1;
+    if (const char* e = getenv("QKAN_ELEM_GR")) force_gr = atoi(e);      // tuning aid: log2 of the lanes per row
+    for (int gr = 0; gr <= 5; ++gr) {
+        if (gr < min_g_log2 && gr < 5) continue;
+        if (force_gr >= 0 && gr != force_gr) continue;
+        const long long G_r = 1ll << gr, passes = (wmax + G_r - 1) / G_r;
+        const double eff = (double)N / (double)(passes * G_r * K);
+        if (force_gr < 0 && best_score >= 0.0 && (gr > 4 || eff < 0.9 * eff_max)) continue;
+        best_score = eff;
+        best.g_r_log2 = gr; best.g_k_log2 = 0; best.passes = (int)passes; best.brows = K; best.efficiency = eff;
+    }
+    return best;
+}
+inline long long elem_steps(const ElemLayout& lay) { return ((long long)lay.brows * lay.passes + 1) << (lay.g_r_log2 + lay.g_k_log2); }
+
+template <typename R>
+QK_HD void fill_elem_step(long long step, const double* W, int N, int K, int D, int passes, int brows, int g_r_log2, int g_k_log2,
+                          CS<R>* we, int* xe) {
+    const int g_log2 = g_r_log2 + g_k_log2;
+    const int g = (int)(step & ((1ll << g_log2) - 1));
+    const long long t = step >> g_log2;
+    const int pi = (int)(t % passes);
+    const long long bi = t / passes;
+    const int k = g >> g_r_log2, r = g & ((1 << g_r_log2) - 1);
+    const long long b = (bi << g_k_log2) + k;
+    long long nf = 0, nl = -1, nl_prev = -1;
+    if (bi < brows && b < K) {
+        elem_row_range(N, K, b, &nf, &nl);
+        if (b > 0) { long long f2; elem_row_range(N, K, b - 1, &f2, &nl_prev); }
+    }
+    const long long n = nf + ((long long)pi << g_r_log2) + r;
+    const bool live = bi < brows && b < K && n <= nl;
+    // a padding step evaluates element 0 (any valid address) and multiplies it by theta = pi rotations: adds exactly 0
+    xe[step] = live ? (int)n | (n > nl_prev ? (1 << 30) : 0) : -1;      // bit 30: the first row that reads the element counts its range violation
+    if (bi >= brows) return;                                            // the padding pass has no SELECT entries
+    for (int j = 0; j < K; ++j) {
+        const long long a = n * K - (long long)N * b + j;
+        const bool on = live && a >= 0 && a < N;
+        for (int d = 0; d <= D; ++d) {
+            CS<R> q;
+            q.c = R(0); q.s = R(1);
+            if (on) {
+                const R w = (R)W[(long long)d * N * K + a + (long long)N * b];
+                q.c = w;
+                q.s = qk_sqrt((R(1) - w) * (R(1) + w));
+            }
+            we[((((t * K) + j) * (D + 1) + d) << g_log2) + g] = q;
+        }
+    }
 }
 
 #if defined(__CUDACC__)
@@ -480,25 +565,20 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const Block
     if (bad) atomicAdd(p.oor, (unsigned long long)bad);
 }
 
-// Window kernel: wide input rows (N784 K10: 6.3 KB of x per sample).  The (lo0, lo2) entries of a sample are built
-// per ROW STEP from the step's input window (block_window) instead of once per sample, so a CTA keeps
-// tile * 2 (W + 1) amplitudes instead of tile * 2 (N + 1) and shared memory no longer limits the resident warps.
-// x is read straight from global memory (each input once per row step that uses it: twice at most, at window
-// boundaries, where its CHEB sequence is evaluated twice).  One sample per lane at a time.
-template <class A, typename R, int NT, int MINB, int DT>
-__global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(const BlockParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int G = p.G, G_r = p.G_r;
-    const int SPC = p.SPC, tile = p.tile, RB = p.row_bytes, W = p.window, plane = p.plane_bytes;
+// Element-owner kernel (see ElemLayout above): no shared memory, SU samples per lane, x read straight from global memory
+// (the G_r lanes of a row read G_r consecutive inputs), the next element's inputs in flight during the current element's
+// arithmetic.  An input shared by two rows (window boundaries) is evaluated by both.
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+__global__ void __launch_bounds__(NT, MINB) qkan_block_elem_kernel(const BlockParams p) {
     constexpr int D1 = DT + 1;
-    char* cs = reinterpret_cast<char*>(smem_raw);
+    const int G = p.G, G_r = p.G_r, SPC = p.SPC;
     const int tid = threadIdx.x;
     const int g = tid & (G - 1);
     const int r = g & (G_r - 1);
     const int k = g >> p.g_r_log2;
     const int slot = tid >> (p.g_r_log2 + p.g_k_log2);
-    const CS<R>* __restrict__ wtab = reinterpret_cast<const CS<R>*>(p.cstab);
-    const int* __restrict__ xotab = p.xotab;
+    const CS<R>* __restrict__ we = reinterpret_cast<const CS<R>*>(p.cstab);
+    const int* __restrict__ xe = p.xotab;
 
     A init[4];
     QK_UNROLL
@@ -506,81 +586,119 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_window_kernel(cons
         init[q].re = (R)p.init[2 * q];
         if constexpr (A::is_complex) init[q].im = (R)p.init[2 * q + 1];
     }
-    {   // the dummy entries (x = 0) never change
-        A d0, d2;
-        cheb_element<A, R, DT>(init, R(0), d0, d2);
-        for (int i = tid; i < tile; i += NT) {
-            *reinterpret_cast<A*>(cs + (size_t)i * RB + W * sizeof(A)) = d0;
-            *reinterpret_cast<A*>(cs + (size_t)i * RB + plane + W * sizeof(A)) = d2;
-        }
-    }
-    const long long n_it = (p.B + tile - 1) / tile;
-    const size_t step_steps = (size_t)p.passes * G;           // table steps of one row step
-    const size_t wstep = (size_t)G * D1;
+    const long long chunk = (long long)SU * SPC;
+    const long long n_chunks = (p.B + chunk - 1) / chunk;
+    const size_t jstep = (size_t)D1 * G;                      // table entries between consecutive j of a lane
+    const int steps_per_row = p.passes * G;
+    unsigned bad = 0;
 
-    for (long long it = blockIdx.x; it < n_it; it += gridDim.x) {
-        const long long s0 = it * tile;
-        const int nsamp = (int)((p.B - s0 < tile) ? (p.B - s0) : tile);
-        const int ls_end = (nsamp + SPC - 1) & ~(SPC - 1);    // whole sub-iterations: the butterfly needs every lane
-        double* const out_t = p.outs[0] + (p.row0 + s0) * p.K;
-        void* const amps_t = p.amps ? (void*)(reinterpret_cast<Cplx<R>*>(p.amps) + s0 * p.K) : nullptr;
-        int prev_hi = -1;
+    for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const long long s0 = c * chunk + slot;                // the lane's samples: s0 + j SPC
+        const long long left = p.B - s0;                      // <= 0: the whole lane is beyond the batch (still runs: the butterfly needs every lane)
+        const double* __restrict__ xs = p.x + (left > 0 ? s0 : 0) * p.N;
+        const int xstride = SPC * p.N;
+        const int* xp = xe + g;
+        const CS<R>* wp = we + g;
+        // the first element's inputs
+        int en = *xp;
+        double xn[SU];
+        QK_UNROLL
+        for (int j = 0; j < SU; ++j) xn[j] = ((long long)j * SPC < left) ? xs[j * xstride + (en < 0 ? 0 : (en & 0xFFFFF))] : 0.0;
         for (int bi = 0; bi < p.brows; ++bi) {
-            int lo, len;
-            block_window(p.N, p.K, p.g_k_log2, bi, &lo, &len);
-            __syncthreads();                                  // the previous row step's entries are consumed
-            // pre-pass over the window of every sample of the tile (flat walk, no division in the loop): range count
-            // (ChebyshevStep.py:46-49; an input shared by two windows is counted once), clip (:52), CHEB sequence
-            unsigned bad = 0;
-            {
-                const int n_in = nsamp * len;
-                int row = tid / len, j = tid - row * len;
-                const int dr = NT / len, dj = NT - dr * len;
-                const double* xw = p.x + s0 * p.N + lo;
-                for (int e = tid; e < n_in; e += NT) {
-                    const double v = xw[(size_t)row * p.N + j];
-                    if (lo + j > prev_hi && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
-                    A lo0, lo2;
-                    cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0, lo2);
-                    *reinterpret_cast<A*>(cs + (size_t)row * RB + j * sizeof(A)) = lo0;
-                    *reinterpret_cast<A*>(cs + (size_t)row * RB + plane + j * sizeof(A)) = lo2;
-                    j += dj;
-                    row += dr;
-                    if (j >= len) { j -= len; ++row; }
+            A acc[SU];
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j) set_amp(acc[j], 0.0);
+            for (int pi = 0; pi < p.passes; ++pi) {
+                const int e_cur = en;
+                double xv[SU];
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) xv[j] = xn[j];
+                xp += G;
+                en = *xp;                                     // next element (the table ends with one pass of padding steps)
+                {
+                    const int off = en < 0 ? 0 : (en & 0xFFFFF);
+                    QK_UNROLL
+                    for (int j = 0; j < SU; ++j) xn[j] = ((long long)j * SPC < left) ? xs[j * xstride + off] : 0.0;
                 }
+                A lo0[SU], lo2[SU];
+                const bool counts = e_cur >= 0 && (e_cur & (1 << 30));
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) {
+                    // range count (ChebyshevStep.py:46-49; once per input), clip (:52), CHEB sequence of the element
+                    const double v = xv[j];
+                    if (counts && (long long)j * SPC < left && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
+                    cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
+                }
+                // SELECT on the element's K (D + 1) blocks (padding entries rotate by pi: they add exactly 0)
+                for (int j = 0; j < p.K; ++j, wp += jstep) select_blocks<A, R, SU, DT>(lo0, lo2, wp, G, acc);
             }
-            prev_hi = lo + len - 1;
-            if (bad) atomicAdd(p.oor, (unsigned long long)bad);
-            __syncthreads();
-
+            // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
             const int b = (bi << p.g_k_log2) + k;
-            const CS<R>* wp0 = wtab + (size_t)bi * step_steps * D1 + g;
-            const int* xp0 = xotab + (size_t)bi * step_steps + g;
-            const int x0 = xp0[0];
-            for (int ls = slot; ls < ls_end; ls += SPC) {
-                const char* row = cs + (size_t)ls * RB;       // idle slots of a ragged tile evolve a stale row; nothing is stored
-                const CS<R>* wp = wp0;
-                const int* xp = xp0;
-                int xo = x0, xprev = -1;
-                A acc[1], lo0[1], lo2[1];
-                set_amp(acc[0], 0.0);
-                for (int pi = 0; pi < p.passes; ++pi) {
-                    if (xo != xprev) {
-                        lo0[0] = *reinterpret_cast<const A*>(row + xo);
-                        lo2[0] = *reinterpret_cast<const A*>(row + plane + xo);
-                        xprev = xo;
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j) {
+                for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[j], shfl_xor_amp(acc[j], m));
+                if (r == 0 && b < p.K && (long long)j * SPC < left) {
+                    const long long o = (s0 + (long long)j * SPC) * p.K + b;
+                    store_result(p, p.row0 * p.K + o, (double)acc[j].re * p.out_scale);
+                    if (p.amps) {
+                        Cplx<R> z;
+                        z.re = (R)((double)acc[j].re * p.amp_scale);
+                        if constexpr (A::is_complex) z.im = (R)((double)acc[j].im * p.amp_scale);
+                        else z.im = R(0);
+                        reinterpret_cast<Cplx<R>*>(p.amps)[o] = z;
                     }
-                    xp += G;
-                    xo = *xp;                                 // next pass (the tables end with one pass of padding steps)
-                    select_blocks<A, R, 1, DT>(lo0, lo2, wp, G, acc);
-                    wp += wstep;
                 }
-                // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
-                for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[0], shfl_xor_amp(acc[0], m));
-                if (ls < nsamp && r == 0 && b < p.K) amajor_store<A, R>(p, acc[0], out_t, amps_t, ls * p.K + b);
             }
         }
     }
+    if (bad) atomicAdd(p.oor, (unsigned long long)bad);
+}
+
+template <typename R>
+__global__ void qkan_prepare_elem_tables_kernel(const double* W, int N, int K, int D, int passes, int brows, int g_r_log2, int g_k_log2,
+                                                long long steps_total, CS<R>* we, int* xe, unsigned long long* bad_weights) {
+    const long long step = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nw = (long long)N * K * (D + 1);
+    unsigned bad = 0;
+    for (long long i = step; i < nw; i += (long long)gridDim.x * blockDim.x)
+        if (!(fabs(W[i]) <= 1.0)) ++bad;                      // MulStep.py:36-37, each weight once
+    if (bad) atomicAdd(bad_weights, (unsigned long long)bad);
+    if (step >= steps_total) return;
+    fill_elem_step<R>(step, W, N, K, D, passes, brows, g_r_log2, g_k_log2, we, xe);
+}
+
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+cudaError_t launch_elem(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p0.D != DT) return cudaErrorInvalidValue;
+    auto kern = qkan_block_elem_kernel<A, R, SU, NT, MINB, DT>;
+    BlockParams p = p0;
+    const int SPC = NT / G;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const long long chunk = (long long)SU * SPC;
+    const long long n_chunks = (p.B + chunk - 1) / chunk;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > n_chunks) grid = n_chunks;
+    if (grid < 1) grid = 1;
+    p.sub = SU; p.tma_ok = 0; p.direct_x = 1; p.s_tot = -1;
+    p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
+    p.SPC = SPC; p.tile = (int)chunk;
+    p.row_bytes = 0; p.plane_bytes = 0;
+    if (grid_out) *grid_out = (int)grid;
+    if (smem_out) *smem_out = 0;
+    kern<<<(unsigned)grid, NT, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+BlockKernelInfo make_elem_info(int is_default) {
+    BlockKernelInfo k;
+    k.amp = AmpId<A>::v;
+    k.mode = 0; k.U = 1; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
+    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 0; k.elem = 1; k.amp_bytes = (int)sizeof(A);
+    k.launch = &launch_elem<A, R, SU, NT, MINB, DT>;
+    return k;
 }
 
 template <typename R>
@@ -667,7 +785,7 @@ BlockKernelInfo make_amajor_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = 0; k.U = 1; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 0; k.amp_bytes = (int)sizeof(A);
+    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 0; k.elem = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_amajor<A, R, SU, NT, MINB, DT>;
     return k;
 }
@@ -701,55 +819,11 @@ BlockKernelInfo make_direct_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = 0; k.U = 1; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 1; k.amp_bytes = (int)sizeof(A);
+    k.tan = 1; k.window = 0; k.amajor = 1; k.direct = 1; k.elem = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_direct<A, R, SU, NT, MINB, DT>;
     return k;
 }
 
-template <class A, typename R, int NT, int MINB, int DT>
-cudaError_t launch_amajor_window(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    if (p0.D != DT || p0.window < 1) return cudaErrorInvalidValue;
-    auto kern = qkan_block_amajor_window_kernel<A, R, NT, MINB, DT>;
-    BlockParams p = p0;
-    const int SPC = NT / G;
-    p.row_bytes = amajor_row_amps(p.window + 1, G, (int)sizeof(A)) * (int)sizeof(A);
-    p.plane_bytes = (p.window + 1) * (int)sizeof(A);
-    int sub = (int)(32768 / ((size_t)SPC * p.row_bytes));      // about 32 KiB of block amplitudes per CTA
-    if (const char* e = getenv("QKAN_BLOCK_SUB")) sub = atoi(e);   // tuning aid
-    if (sub > 32) sub = 32;
-    if (sub < 1) sub = 1;
-    auto smem_for = [&](int sb) { return amajor_window_smem_bytes(SPC, p.row_bytes, sb); };
-    while (sub > 1 && smem_for(sub) > AMAJOR_SMEM_CAP) --sub;
-    if (smem_for(sub) > AMAJOR_SMEM_CAP) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_for(sub));
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem_for(sub));
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    const long long resident = (long long)sm_count * per_sm;
-    while (sub > 1 && (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub) < 4 * resident) sub >>= 1;
-    const long long n_it = (p.B + (long long)SPC * sub - 1) / ((long long)SPC * sub);
-    long long grid = resident < n_it ? resident : n_it;
-    if (grid < 1) grid = 1;
-    p.sub = sub;
-    p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
-    p.SPC = SPC; p.tile = SPC * sub;
-    p.tma_ok = 0; p.direct_x = 1; p.s_tot = -1;
-    if (grid_out) *grid_out = (int)grid;
-    if (smem_out) *smem_out = (int)smem_for(sub);
-    kern<<<(unsigned)grid, NT, smem_for(sub), stream>>>(p);
-    return cudaGetLastError();
-}
-template <class A, typename R, int NT, int MINB, int DT>
-BlockKernelInfo make_amajor_window_info(int is_default) {
-    BlockKernelInfo k;
-    k.amp = AmpId<A>::v;
-    k.mode = 0; k.U = 1; k.SU = 1; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 1; k.window = 1; k.amajor = 1; k.direct = 0; k.amp_bytes = (int)sizeof(A);
-    k.launch = &launch_amajor_window<A, R, NT, MINB, DT>;
-    return k;
-}
 #endif  // __CUDACC__
 
 }  // namespace qkan

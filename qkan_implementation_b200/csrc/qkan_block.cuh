@@ -675,6 +675,7 @@ struct BlockKernelInfo {
     int amajor;                 // a-major tables (qkan_amajor.cuh): D + 1 SELECT entries per (row step, pass, lane)
     int amp_bytes;              // a-major kernels: sizeof(amplitude), the entry size of the cs planes
     int direct;                 // direct kernel (qkan_amajor.cuh): every output row reads one input element, no shared memory
+    int elem;                   // element-owner kernel (qkan_amajor.cuh): wide input rows, lanes own input elements, no shared memory
     int is_default;
     cudaError_t (*launch)(const BlockParams&, int g, int sm_count, cudaStream_t, int* grid_out, int* smem_out);
 };
@@ -751,7 +752,7 @@ BlockKernelInfo make_block_info(int is_default) {
     BlockKernelInfo k;
     k.amp = AmpId<A>::v;
     k.mode = MODE; k.U = U; k.SU = SU; k.NT = NT; k.MINB = MINB; k.DT = DT; k.is_default = is_default;
-    k.tan = 0; k.window = 0; k.amajor = 0; k.direct = 0; k.amp_bytes = (int)sizeof(A);
+    k.tan = 0; k.window = 0; k.amajor = 0; k.direct = 0; k.elem = 0; k.amp_bytes = (int)sizeof(A);
     k.launch = &launch_block<A, R, U, SU, MODE, NT, MINB, DT>;
     return k;
 }

@@ -138,10 +138,10 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // two samples per lane share every SELECT entry and the per-pass bookkeeping: pays for shallow sequences
         const int want_SU = fSU ? fSU : 2;                     // tile kernel
         const int want_SU_direct = fSU ? fSU : 4;              // direct kernel (profiles/r02e_tune_direct.jsonl)
-        auto find_amajor = [&](int NT, int SU, bool window_kernel, bool direct_kernel = false) -> const BlockKernelInfo* {
+        auto find_amajor = [&](int NT, int SU, bool window_kernel, bool direct_kernel = false, bool elem_kernel = false) -> const BlockKernelInfo* {
             for (const BlockKernelInfo& k : block_registry()) {
-                if (!k.amajor || (k.window != 0) != window_kernel || (k.direct != 0) != direct_kernel || k.amp != dtype ||
-                    k.DT != max_degree || k.NT != NT) continue;
+                if (!k.amajor || (k.window != 0) != window_kernel || (k.direct != 0) != direct_kernel || (k.elem != 0) != elem_kernel ||
+                    k.amp != dtype || k.DT != max_degree || k.NT != NT) continue;
                 if (!window_kernel && k.SU != SU) continue;
                 if (fMINB ? (k.MINB != fMINB) : !k.is_default) continue;
                 return &k;
@@ -151,7 +151,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // resident warps per SM that the shared memory of one CTA allows (registers cap it at 32 / 24)
         auto warps_for = [](size_t smem, int NT) { return (int)((220 * 1024 / (smem + 1024)) * (size_t)(NT / 32)); };
         // rows that read a single input element: the direct kernel (no shared memory)
-        if (amajor_ok && !getenv("QKAN_BLOCK_NO_DIRECT") && !getenv("QKAN_BLOCK_FORCE_WINDOW")) {
+        const bool force_elem = getenv("QKAN_BLOCK_FORCE_ELEM") != nullptr;      // A/B aid
+        if (amajor_ok && !getenv("QKAN_BLOCK_NO_DIRECT") && !force_elem) {
             const BlockLayout cand = plan_amajor_layout(N, K, 0);
             if (amajor_direct_ok(N, K, cand)) {
                 const int NTs[2] = {256, 128};
@@ -164,10 +165,25 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                 }
             }
         }
-        // pass 0 wants >= 24 resident warps (the FP64 pipe needs them to stay busy), pass 1 takes whatever launches
+        // Rows that read several inputs.  Pass 0: the element-owner kernel when its walk wastes little (rows much wider than
+        // K: measured faster than the tile kernel on every such shape, profiles/r02j_tune_c4.jsonl), else the tile kernel
+        // when shared memory leaves >= 24 resident warps; pass 1: whatever launches.
         for (int pass = 0; pass < 2 && amajor_ok && !bbest; ++pass) {
+            if (!getenv("QKAN_BLOCK_NO_ELEM") && (!fNT || fNT == 256)) {
+                const ElemLayout el = plan_elem_layout(N, K, 0);
+                if (force_elem || el.efficiency >= (pass == 0 ? 0.8 : 0.0)) {
+                    for (int SU = fSU ? fSU : 4; SU >= 1 && !bbest; SU >>= 1) {
+                        const BlockKernelInfo* k = find_amajor(256, SU, false, false, true);
+                        if (k) {
+                            bbest = k;
+                            lay.U = 1; lay.g_r_log2 = el.g_r_log2; lay.g_k_log2 = el.g_k_log2; lay.passes = el.passes; lay.brows = el.brows;
+                            lay.efficiency = el.efficiency;
+                        }
+                    }
+                }
+            }
             const int NTs[2] = {256, 128};
-            for (int ni = 0; ni < 2 && !bbest && !getenv("QKAN_BLOCK_FORCE_WINDOW"); ++ni) {
+            for (int ni = 0; ni < 2 && !bbest && !force_elem; ++ni) {
                 const int NT = NTs[ni];
                 if (fNT && NT != fNT) continue;
                 for (int min_g = 0; min_g <= 5 && !bbest; ++min_g) {
@@ -183,23 +199,6 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
                         if (k) { bbest = k; lay = cand; }
                     }
                 }
-            }
-            // wide input rows: the window kernel builds the triples per row step from the step's input window
-            // (N784 K10 D5).  Narrowest lane group whose window tile leaves room for four (else three) 256-thread
-            // CTAs per SM; rows in parallel capped first at 1, then 2, ... (the window grows with them)
-            if (fNT && fNT != 256) continue;
-            if (getenv("QKAN_BLOCK_NO_WINDOW")) continue;
-            for (int want = pass == 0 ? 32 : 8; want >= (pass == 0 ? 24 : 8) && !bbest; want -= 8)
-            for (int gkm = 0; gkm <= 5 && !bbest; ++gkm)
-            for (int mg = 0; mg <= 5 && !bbest; ++mg) {
-                const BlockLayout c = plan_amajor_layout(N, K, mg, gkm);
-                const int G = 1 << (c.g_r_log2 + c.g_k_log2);
-                if (G < (1 << mg) || c.efficiency < 0.9) continue;
-                const int W = block_window_max(N, K, c.g_k_log2, c.brows);
-                const size_t win_cs = amajor_window_smem_bytes(256 / G, amajor_row_amps(W + 1, G, asz) * asz, 1);
-                if (win_cs > AMAJOR_SMEM_CAP || warps_for(win_cs, 256) < want) continue;
-                const BlockKernelInfo* k = find_amajor(256, 1, true);
-                if (k) { bbest = k; lay = c; window = W; }
             }
         }
         // ---- generic (cos, sin) kernels: paper mode, D = 0, D > 16, or rows too wide for the above
@@ -231,8 +230,8 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
             }
         }
         if (getenv("QKAN_DEBUG_SELECT") && bbest)
-            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> direct=%d amajor=%d U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
-                    N, K, max_degree, dtype, bbest->direct, bbest->amajor, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
+            fprintf(stderr, "qkan select: N=%d K=%d D=%d dtype=%d -> elem=%d direct=%d amajor=%d U=%d SU=%d NT=%d MINB=%d DT=%d tan=%d window=%d (W=%d) g_r=%d g_k=%d passes=%d rows=%d\n",
+                    N, K, max_degree, dtype, bbest->elem, bbest->direct, bbest->amajor, bbest->U, bbest->SU, bbest->NT, bbest->MINB, bbest->DT, bbest->tan, bbest->window, window,
                     lay.g_r_log2, lay.g_k_log2, lay.passes, lay.brows);
         if (!bbest) {
             char buf[160];
@@ -281,7 +280,7 @@ extern "C" int qkan_layer_create(qkan_layer** out, int N, int K, int max_degree,
         // (+ 8 more, never read: the window kernel's L1 prefetches run WINDOW_PREFETCH passes ahead)
         const size_t slots = ((size_t)l->lay.brows * l->lay.passes + 1 + 8) * l->lay.U * G;
         // a-major tables: D + 1 SELECT entries per (row step, pass, lane) step
-        const size_t per_slot = l->bkern->amajor ? (size_t)(max_degree + 1) : 1;
+        const size_t per_slot = l->bkern->elem ? (size_t)K * (max_degree + 1) : (l->bkern->amajor ? (size_t)(max_degree + 1) : 1);
         e = cudaMalloc(&l->wtab, slots * per_slot * 2 * amp_real_size(dtype));
         if (e == cudaSuccess) e = cudaMalloc(&l->xidx, slots * sizeof(int));
     } else {
@@ -341,16 +340,26 @@ extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_dev
                            stream));
     const double* Wd = l->W_dev;
     CU(cudaMemsetAsync(l->counters + 1, 0, sizeof(unsigned long long), stream));
-    if (l->engine == 0 && l->bkern->amajor) {
+    if (l->engine == 0 && l->bkern->elem) {
+        ElemLayout el{l->lay.g_r_log2, l->lay.g_k_log2, l->lay.passes, l->lay.brows, l->lay.efficiency};
+        const long long steps = elem_steps(el);
+        const unsigned nt = 128, nb = (unsigned)((steps + nt - 1) / nt);
+        if (l->dtype == QKAN_COMPLEX64)
+            qkan_prepare_elem_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, el.passes, el.brows, el.g_r_log2,
+                                                                          el.g_k_log2, steps, (CS<float>*)l->wtab, l->xidx, l->counters + 1);
+        else
+            qkan_prepare_elem_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, el.passes, el.brows, el.g_r_log2,
+                                                                           el.g_k_log2, steps, (CS<double>*)l->wtab, l->xidx, l->counters + 1);
+    } else if (l->engine == 0 && l->bkern->amajor) {
         const long long steps = amajor_steps(l->lay);
         const unsigned nt = 128, nb = (unsigned)((steps + nt - 1) / nt);
         if (l->dtype == QKAN_COMPLEX64)
             qkan_prepare_amajor_tables_kernel<float><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
-                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, l->window, steps,
+                                                                            l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, 0, steps,
                                                                             (CS<float>*)l->wtab, l->xidx, l->counters + 1);
         else
             qkan_prepare_amajor_tables_kernel<double><<<nb, nt, 0, stream>>>(Wd, l->N, l->K, l->D, l->lay.passes, l->lay.brows,
-                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, l->window, steps,
+                                                                             l->lay.g_r_log2, l->lay.g_k_log2, l->bkern->amp_bytes, 0, steps,
                                                                              (CS<double>*)l->wtab, l->xidx, l->counters + 1);
     } else if (l->engine == 0) {
         const long long G = 1ll << (l->lay.g_r_log2 + l->lay.g_k_log2);
@@ -399,7 +408,7 @@ static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, voi
         p.B = B; p.N = l->N; p.K = l->K; p.D = l->D;
         p.g_r_log2 = l->lay.g_r_log2; p.g_k_log2 = l->lay.g_k_log2;
         p.passes = l->lay.passes; p.brows = l->lay.brows;
-        p.sub = 1; p.tma_ok = 0; p.direct_x = 0; p.window = l->window;
+        p.sub = 1; p.tma_ok = 0; p.direct_x = 0; p.window = 0;
         p.plane_bytes = 0;
         p.plain = (p.n_out == 1 && !p.mc_out && !amps) ? 1 : 0;
         for (int q = 0; q < 8; ++q) p.init[q] = 0.0;
@@ -681,6 +690,15 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
             double elems = (double)l->N;
             if (k.direct) elems = (double)l->K;               // every row evaluates its own element
             info->direct_rows = k.direct;
+            info->element_owner = k.elem;
+            if (k.elem) {                                     // every row evaluates the elements it reads
+                elems = 0.0;
+                for (long long b = 0; b < l->K; ++b) {
+                    long long f, la;
+                    elem_row_range(l->N, l->K, b, &f, &la);
+                    elems += (double)(la - f + 1);
+                }
+            }
             if (l->window) {
                 elems = 0.0;
                 for (int bi = 0; bi < l->lay.brows; ++bi) {

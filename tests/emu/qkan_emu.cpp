@@ -351,6 +351,76 @@ extern "C" int qkan_emu_direct_forward(int amp, const double* x, const double* W
     return -2;
 }
 
+// element-owner kernel (wide input rows): lanes own input elements; tables, element walk, padding, butterfly
+template <class A, typename R>
+int emu_elem(const double* x, const double* W, long long B, int N, int K, int D, int min_g, double* out, double* amps, long long* counted) {
+    if (D < TAN_MIN_DT || D > TAN_MAX_DT) return -4;
+    const ElemLayout lay = plan_elem_layout(N, K, min_g);
+    const int G_r = 1 << lay.g_r_log2, G_k = 1 << lay.g_k_log2, G = G_r * G_k;
+    const long long steps = elem_steps(lay);
+    std::vector<CS<R>> we((size_t)lay.brows * lay.passes * K * (D + 1) * G);
+    std::vector<int> xe(steps);
+    for (long long e = 0; e < steps; ++e)
+        fill_elem_step<R>(e, W, N, K, D, lay.passes, lay.brows, lay.g_r_log2, lay.g_k_log2, we.data(), xe.data());
+    int NA = 0, NB = 0, L = 0;
+    while ((1 << NA) < N) ++NA;
+    while ((1 << NB) < K) ++NB;
+    while ((1 << L) < D + 1) ++L;
+    const double amp_scale = std::pow(2.0, -0.5 * (NA + NB + 2 * L + NA));
+    A init[4];
+    for (int q = 0; q < 4; ++q) set_amp(init[q], q == 0 ? 1.0 : 0.0);
+    long long cnt = 0;
+    for (long long s = 0; s < B; ++s)
+        for (int bi = 0; bi < lay.brows; ++bi)
+            for (int k = 0; k < G_k; ++k) {
+                const int b = bi * G_k + k;
+                std::vector<A> acc(G_r);
+                for (int r = 0; r < G_r; ++r) {
+                    A a1[1];
+                    set_amp(a1[0], 0.0);
+                    const int g = k * G_r + r;
+                    for (int pi = 0; pi < lay.passes; ++pi) {
+                        const size_t t = (size_t)bi * lay.passes + pi;
+                        const int en = xe[t * G + g];
+                        const int n = en < 0 ? 0 : (en & 0xFFFFF);
+                        if (n >= N) return -8;
+                        if (s == 0 && en >= 0 && (en & (1 << 30))) ++cnt;
+                        A lo0[1], lo2[1];
+                        ChebRun<A, R, 16>::go(D, init, clip_unit<R>(x[s * N + n]), lo0[0], lo2[0]);
+                        for (int j = 0; j < K; ++j) SelectRun<A, R, 16>::go(D, lo0, lo2, we.data() + ((t * K + j) * (D + 1)) * G + g, G, a1);
+                    }
+                    acc[r] = a1[0];
+                }
+                for (int m = G_r >> 1; m >= 1; m >>= 1) {
+                    std::vector<A> nxt(acc);
+                    for (int r = 0; r < G_r; ++r) add_amp(nxt[r], acc[r ^ m]);
+                    acc = nxt;
+                }
+                if (b < K) {
+                    out[s * K + b] = (double)acc[0].re / ((double)N * (D + 1));
+                    if (amps) {
+                        amps[2 * (s * K + b)] = (double)acc[0].re * amp_scale;
+                        if constexpr (A::is_complex) amps[2 * (s * K + b) + 1] = (double)acc[0].im * amp_scale;
+                        else amps[2 * (s * K + b) + 1] = 0.0;
+                    }
+                }
+            }
+    if (counted) *counted = cnt;                              // elements flagged "count the range violation here": must be N
+    return 0;
+}
+extern "C" int qkan_emu_elem_forward(int amp, int min_g, const double* x, const double* W, long long B, int N, int K, int D, double* out,
+                                     double* amps, long long* counted) {
+    if (amp == 0) return emu_elem<Cplx<double>, double>(x, W, B, N, K, D, min_g, out, amps, counted);
+    if (amp == 1) return emu_elem<Cplx<float>, float>(x, W, B, N, K, D, min_g, out, amps, counted);
+    if (amp == 2) return emu_elem<Real<double>, double>(x, W, B, N, K, D, min_g, out, amps, counted);
+    return -2;
+}
+extern "C" void qkan_emu_elem_layout(int N, int K, int min_g, int* out4, double* eff) {
+    const ElemLayout l = plan_elem_layout(N, K, min_g);
+    out4[0] = l.g_r_log2; out4[1] = l.g_k_log2; out4[2] = l.passes; out4[3] = l.brows;
+    *eff = l.efficiency;
+}
+
 extern "C" int qkan_emu_amajor_forward(int amp, int min_g, int max_gk, int window_mode, const double* x, const double* W,
                                        long long B, int N, int K, int D, double* out, double* amps) {
     if (amp == 0) return emu_amajor<Cplx<double>, double>(x, W, B, N, K, D, min_g, max_gk, window_mode, out, amps);

@@ -121,6 +121,31 @@ def test_emulated_direct_kernel_matches_oracle(emu, N, K, D):
     assert f(0, x.ctypes.data, W.ctypes.data, B, 3, 4, D, out.ctypes.data, amps.ctypes.data) == -9      # K not a multiple of N
 
 
+@pytest.mark.parametrize("min_g", [0, 2, 5])
+@pytest.mark.parametrize("N,K,D", [(784, 10, 5), (100, 10, 5), (33, 3, 2), (7, 1, 3), (8, 4, 2), (5, 8, 1), (4, 4, 3), (600, 16, 4), (13, 7, 16), (1, 5, 2), (64, 64, 1)])
+def test_emulated_element_owner_kernel_matches_oracle(emu, N, K, D, min_g):
+    """Element-owner walk (qkan_block_elem_kernel): layout planner, element / SELECT tables with padding, one range count per
+    input, xor-butterfly read-out; lane by lane."""
+    import ctypes
+    f = emu.qkan_emu_elem_forward
+    f.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 3
+    rng = np.random.default_rng(N * 13 + K * 5 + D + min_g)
+    B = 2
+    x = rng.uniform(-1.2, 1.2, (B, N))
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    spec = o.circuit_spec(N, K, D)
+    ref = o.forward_closed_form(x, W, N, K, D, "compat")
+    for amp, tol in ((0, 1e-14), (1, 1e-5), (2, 1e-14)):
+        out = np.zeros((B, K))
+        amps = np.zeros((B, K, 2))
+        counted = ctypes.c_longlong(-1)
+        assert f(amp, min_g, x.ctypes.data, W.ctypes.data, B, N, K, D, out.ctypes.data, amps.ctypes.data, ctypes.byref(counted)) == 0
+        assert np.abs(out - ref).max() <= tol
+        assert np.abs(amps[..., 0] * spec.out_scale - ref).max() <= tol
+        assert np.abs(amps[..., 1]).max() == 0.0
+        assert counted.value == N                      # every input's range violation is reported by exactly one (row, lane)
+
+
 def test_amajor_row_strides_spread_the_lanes(emu):
     """amajor_row_amps: the lanes of one shared-memory phase (128 bytes) - P / G sample rows x G consecutive amplitudes of a
     plane - land on different slots for the small power-of-two groups; rows hold both planes."""

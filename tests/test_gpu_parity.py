@@ -182,8 +182,8 @@ def test_oracle_parity_seeded(Q, N, K, D):
 
 
 @pytest.mark.parametrize("N,K,D", [(784, 10, 5), (1000, 3, 2), (600, 16, 4), (2000, 1, 3), (513, 7, 16), (900, 33, 2), (100, 10, 5)])
-def test_window_kernel_wide_rows(Q, N, K, D):
-    """Wide input rows run the window kernel (rotation entries built per row step from the step's input window)."""
+def test_wide_input_rows(Q, N, K, D):
+    """Wide input rows run the element-owner kernel (lanes own input elements; an input read by two rows is counted once)."""
     rng = np.random.default_rng(N + 3 * K + D)
     B = 61                                    # ragged
     x = rng.uniform(-1.1, 1.1, (B, N))
@@ -196,8 +196,7 @@ def test_window_kernel_wide_rows(Q, N, K, D):
         layer = Q.QKANLayer(N, K, D, dtype=dtype)
         y, a = layer.forward(x, W, return_amplitudes=True)
         info = layer.kernel_info()
-        if K > 1:                                          # K = 1: the one output row reads every input, no window to cut
-            assert info["scaled_rotations"] == 1, info
+        assert info["scaled_rotations"] == 1 and info["element_owner"] == 1, info
         assert_close(y, ref, dtype)
         layer.forward(torch.from_numpy(x).cuda(), W)       # device input: the count stays for the caller
         assert layer.out_of_range_count() == n_bad         # an input shared by two windows is counted once
@@ -365,9 +364,11 @@ def test_special_input_values(Q, N, K, D):
 
 @pytest.mark.parametrize("env", [{"QKAN_BLOCK_TUNE": "1:256:4:1"}, {"QKAN_BLOCK_TUNE": "1:256:3:2"}, {"QKAN_BLOCK_TUNE": "1:256:2:4"},
                                  {"QKAN_BLOCK_TUNE": "1:128:8:1"}, {"QKAN_BLOCK_TUNE": "4:128:4:1"}, {"QKAN_BLOCK_NO_DT": "1"},
-                                 {"QKAN_BLOCK_NO_DIRECT": "1"}, {"QKAN_BLOCK_FORCE_WINDOW": "1"},
+                                 {"QKAN_BLOCK_NO_DIRECT": "1"}, {"QKAN_BLOCK_FORCE_ELEM": "1"}, {"QKAN_BLOCK_NO_ELEM": "1"}, {"QKAN_ELEM_GR": "2"}, {"QKAN_ELEM_GR": "5"},
+                                 {"QKAN_BLOCK_FORCE_ELEM": "1", "QKAN_BLOCK_TUNE": "1:256:3:2"}, {"QKAN_BLOCK_FORCE_ELEM": "1", "QKAN_BLOCK_TUNE": "1:256:4:1"},
                                  {"QKAN_BLOCK_STRIDED": "1"}, {"QKAN_BLOCK_STRIDED": "0"}, {"QKAN_BLOCK_SUB": "1"},
-                                 {"QKAN_BLOCK_SUB": "2"}, {"QKAN_BLOCK_NO_WINDOW": "1"}, {"QKAN_HOST_PATH": "staged"}])
+                                 {"QKAN_BLOCK_SUB": "2"}, {"QKAN_HOST_PATH": "staged"}, {"QKAN_HOST_PATH": "zero_copy"}, {"QKAN_HOST_PATH": "copy_out"},
+                                 {"QKAN_HOST_NO_GRAPH": "1"}])
 def test_tuning_variants_agree(Q, env, monkeypatch):
     """Every kernel variant / schedule reachable through the tuning knobs gives the oracle's numbers on ragged batches
     (the knobs are read at layer creation / launch)."""

@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from qkan_implementation_b200 import QKANLayer, _binding  # noqa: E402
 
-CONFIGS = {"c2": (4, 4, 3, 1_000_000), "c5d1": (8, 8, 1, 1_000_000), "c5d2": (8, 8, 2, 1_000_000), "c5d4": (8, 8, 4, 500_000),
+CONFIGS = {"c4b": (784, 10, 5, 100_000), "c2": (4, 4, 3, 1_000_000), "c5d1": (8, 8, 1, 1_000_000), "c5d2": (8, 8, 2, 1_000_000), "c5d4": (8, 8, 4, 500_000),
            "c5d8": (8, 8, 8, 200_000), "c5d16": (8, 8, 16, 100_000), "c3": (16, 16, 8, 50_000), "c4": (784, 10, 5, 20_000)}
 
 

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
             char* dst = pre_dst0;
             for (int e = tid; e < n_in; e += NT) {
                 const double v = xs[e];
-                if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
+                if (!(fabs(v) <= 1.0 + 1e-8)) ++bad;
                 A lo0, lo2;
                 cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0, lo2);
                 *reinterpret_cast<A*>(dst) = lo0;
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const Block
         for (int j = 0; j < SU; ++j) {
             // range count (the reference prints a warning, ChebyshevStep.py:46-49), clip (:52), CHEB sequence of the element
             const double v = xv[j];
-            if ((!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) && counts && (full || (long long)j * SPC < left)) ++bad;
+            if (!(fabs(v) <= 1.0 + 1e-8) && counts && (full || (long long)j * SPC < left)) ++bad;
             cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
             set_amp(acc[j], 0.0);
         }
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_elem_kernel(const BlockPa
                 for (int j = 0; j < SU; ++j) {
                     // range count (ChebyshevStep.py:46-49; once per input), clip (:52), CHEB sequence of the element
                     const double v = xv[j];
-                    if (counts && (long long)j * SPC < left && (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8))) ++bad;
+                    if (counts && (long long)j * SPC < left && !(fabs(v) <= 1.0 + 1e-8)) ++bad;
                     cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
                 }
                 // SELECT on the element's K (D + 1) blocks (padding entries rotate by pi: they add exactly 0)

@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_kernel(const BlockParams 
             int row = pre_row0, n = pre_n0;
             for (int e = tid; e < n_in; e += NT) {
                 const double v = xs[e];
-                if (!(-1.0 - 1e-8 <= v) || !(v <= 1.0 + 1e-8)) ++bad;
+                if (!(fabs(v) <= 1.0 + 1e-8)) ++bad;
                 const R c = clip_unit<R>(v);
                 CS<R> en;
                 en.c = c;

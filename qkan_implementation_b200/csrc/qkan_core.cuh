@@ -219,8 +219,8 @@ struct TileArgs {
 };
 
 template <typename R> QK_HD R clip_unit(double x) {
-    // comparisons (not fmin/fmax) so that NaN propagates like np.clip (ChebyshevStep.py:52)
-    double y = x < -1.0 ? -1.0 : (x > 1.0 ? 1.0 : x);
+    // one comparison on |x| (not fmin/fmax), so that NaN propagates like np.clip (ChebyshevStep.py:52)
+    const double y = fabs(x) > 1.0 ? copysign(1.0, x) : x;
     return (R)y;
 }
 

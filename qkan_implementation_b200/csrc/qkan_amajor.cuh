@@ -139,22 +139,40 @@ inline size_t amajor_smem_bytes(int N, int SPC, int row_bytes, int SU, int sub) 
 }
 constexpr size_t AMAJOR_SMEM_CAP = 200 * 1024;
 
-// CHEB on one input element: the block state `init` through D applications of Ry(theta_x), cos(theta_x / 2) = c,
-// in the scaled form (D - 1 full passes M(t), then the pruned pass alpha u + beta v with gamma^D and the quarter
-// turns); returns the f_x = 0 amplitudes of the two f_w halves.
+// CHEB on one input element: the block state `init` through D applications of Ry(theta_x), cos(theta_x / 2) = c;
+// returns the f_x = 0 amplitudes of the two f_w halves.
+//   D >= 3: scaled form - D - 1 full passes M(t) (8 FMA), then the pruned pass alpha u + beta v with gamma^D and the
+//           quarter turns (4 MUL + 4 FMA); the conversion of c into (t, alpha, beta) costs one reciprocal square root and
+//           about 24 FP64 instructions + 14 selects per element;
+//   D <= 2: plain (cos, sin) rotations - D - 1 full passes (8 MUL + 8 FMA), then the pruned pass (4 MUL + 4 FMA); the
+//           conversion is one square root.  8 + 16 (D - 1) + 8 against 24 + 8 (D - 1) + 8
+//           FP64 instructions and no selects: measured faster at D = 1, 2 (N8 K8, 10 M: +4.5 %, +2 %), slower at D = 3 (-3.6 %; N4 K4 D3 -4 %): profiles/r02p_bench_cs_form_d3.json.
+constexpr int CS_FORM_MAX_DT = 2;
+constexpr bool cheb_uses_cs_form(int DT) { return DT <= CS_FORM_MAX_DT; }
 template <class A, typename R, int DT>
 QK_HD void cheb_element(const A (&init)[4], R c, A& lo0, A& lo2) {
-    const TanEntry<R> e = tan_entry<R>(c, DT);
     A v[4];
     QK_UNROLL
     for (int q = 0; q < 4; ++q) v[q] = init[q];
-    QK_UNROLL
-    for (int r = 0; r + 1 < DT; ++r) {
-        rot_tan(v[0], v[1], e.t);
-        rot_tan(v[2], v[3], e.t);
+    if constexpr (cheb_uses_cs_form(DT)) {
+        const R s = qk_sqrt((R(1) - c) * (R(1) + c));
+        QK_UNROLL
+        for (int r = 0; r + 1 < DT; ++r) {
+            rot(v[0], v[1], c, s);
+            rot(v[2], v[3], c, s);
+        }
+        lo0 = rot_lo(v[0], v[1], c, s);
+        lo2 = rot_lo(v[2], v[3], c, s);
+    } else {
+        const TanEntry<R> e = tan_entry<R>(c, DT);
+        QK_UNROLL
+        for (int r = 0; r + 1 < DT; ++r) {
+            rot_tan(v[0], v[1], e.t);
+            rot_tan(v[2], v[3], e.t);
+        }
+        lo0 = lin2(v[0], v[1], e.al, e.be);
+        lo2 = lin2(v[2], v[3], e.al, e.be);
     }
-    lo0 = lin2(v[0], v[1], e.al, e.be);
-    lo2 = lin2(v[2], v[3], e.al, e.be);
 }
 
 // SELECT on the D + 1 degree copies of SU samples' (a, b) block, fused with the read-out sum:

@@ -7,6 +7,7 @@
 #include "../../include/qkan_b200.h"
 
 #include <cstdio>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -53,6 +54,13 @@ int clog2(int n) {
 }
 
 constexpr int MAX_CHUNKS = 64;
+
+// NVTX range around the host side of an entry point (visible in Nsight Systems / ncu --nvtx; header-only NVTX 3: no cost
+// when no tool is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // every entry point runs on the layer's device and leaves the caller's current device as it found it
 struct DeviceGuard {
@@ -316,6 +324,7 @@ extern "C" void qkan_layer_destroy(qkan_layer* l) {
 }
 
 extern "C" int qkan_layer_set_weights(qkan_layer* l, const double* W, int on_device, int validate, void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_set_weights");
     if (!l || !W) return fail(QKAN_ERR_BAD_SHAPE, "null layer or weights");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     ON_DEVICE(l->device);
@@ -432,6 +441,7 @@ static int launch_on(qkan_layer* l, const double* x, int64_t B, double* out, voi
 }
 
 extern "C" int qkan_layer_forward(qkan_layer* l, const double* x, int64_t B, double* out, void* amps, void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_forward");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
@@ -471,6 +481,7 @@ static int ensure_host_path(qkan_layer* l, int64_t B, bool want_amps) {
 
 extern "C" int qkan_layer_forward_peers(qkan_layer* l, const double* x, int64_t B, void* const* out_ptrs, int n_ptrs,
                                         int64_t row_offset, void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_forward_peers");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0 || row_offset < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch / row offset");
     if (!out_ptrs || n_ptrs < 1 || n_ptrs > 8) return fail(QKAN_ERR_BAD_SHAPE, "need 1..8 result buffers");
@@ -485,6 +496,7 @@ extern "C" int qkan_layer_forward_peers(qkan_layer* l, const double* x, int64_t 
 
 extern "C" int qkan_layer_forward_multicast(qkan_layer* l, const double* x, int64_t B, void* mc_out, int64_t row_offset,
                                             void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_forward_multicast");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0 || row_offset < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch / row offset");
     if (!mc_out) return fail(QKAN_ERR_BAD_SHAPE, "null multicast pointer");
@@ -497,6 +509,7 @@ extern "C" int qkan_layer_forward_multicast(qkan_layer* l, const double* x, int6
 }
 
 extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B, double* out, void* amps) {
+    NvtxRange nvtx_range("qkan_layer_forward_host");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "forward called before set_weights");
@@ -709,8 +722,14 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
             }
             info->degree_factored = 1;
             info->cheb_elements = (int)elems;
-            info->flops_exec = cf * (elems * (16.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
-            info->fp_inst_exec = cf * (elems * 8.0 * Dd + 4.0 * (double)info->blocks);
+            if (cheb_uses_cs_form(l->D)) {                    // plain (cos, sin) rotations below four applications
+                info->scaled_rotations = 0;
+                info->flops_exec = cf * (elems * (24.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
+                info->fp_inst_exec = cf * (elems * (16.0 * (Dd - 1.0) + 8.0) + 4.0 * (double)info->blocks);
+            } else {
+                info->flops_exec = cf * (elems * (16.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
+                info->fp_inst_exec = cf * (elems * 8.0 * Dd + 4.0 * (double)info->blocks);
+            }
             info->flops_per_block_basis = cf * (double)info->blocks * (16.0 * Dd + 4.0);
         }
         info->layout_efficiency = l->lay.efficiency;
@@ -759,6 +778,7 @@ __global__ void qkan_diagonals_kernel(const double* x, const double* W, long lon
 
 extern "C" int qkan_layer_diagonals(qkan_layer* l, const double* x, int64_t B, double* cheb, double* weighted,
                                     double* lcu, void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_diagonals");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "diagonals called before set_weights");
@@ -837,6 +857,7 @@ __global__ void qkan_stage_snapshot_kernel(const double* x, const double* W, lon
 
 extern "C" int qkan_layer_stage_snapshots(qkan_layer* l, const double* x, int64_t B, double* cheb, double* weighted,
                                           double* lcu, void* cuda_stream) {
+    NvtxRange nvtx_range("qkan_layer_stage_snapshots");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
     if (B < 0) return fail(QKAN_ERR_BAD_SHAPE, "negative batch");
     if (!l->weights_set) return fail(QKAN_ERR_NO_WEIGHTS, "stage snapshots called before set_weights");

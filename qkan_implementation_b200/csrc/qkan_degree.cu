@@ -474,7 +474,7 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
     // register accumulators for X^T r when a lane's share (ceil(F / 32) features x (D+1)^2) fits 64 doubles
 #define QK_RES_CASE(DD)                                                                                                              \
     case DD:                                                                                                                         \
-        if (jf == 1 && 1 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, 1)                                                \
+        if (jf == 1 && 1 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (1 * (DD + 1) * (DD + 1) <= 64 ? 1 : 0))          \
         else if (jf == 2 && 2 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (2 * (DD + 1) * (DD + 1) <= 64 ? 2 : 0))     \
         else if (jf == 3 && 3 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (3 * (DD + 1) * (DD + 1) <= 64 ? 3 : 0))     \
         else if (jf == 4 && 4 * (DD + 1) * (DD + 1) <= 64) QK_RES_LAUNCH(DD + 1, (4 * (DD + 1) * (DD + 1) <= 64 ? 4 : 0))     \

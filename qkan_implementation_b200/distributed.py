@@ -32,6 +32,8 @@ def gather_outputs(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
     sizes = shard_sizes(B, world)
     mx = max(sizes) if sizes else 0
     K = local.shape[1]
+    if local.is_cuda:
+        torch.cuda.nvtx.range_push("qkan gather_outputs (NCCL all_gather)")
     if local.shape[0] < mx:
         pad = torch.zeros((mx - local.shape[0], K), dtype=local.dtype, device=local.device)
         local = torch.cat([local, pad], dim=0)
@@ -42,6 +44,8 @@ def gather_outputs(local: torch.Tensor, B: int, group=None) -> torch.Tensor:
         parts = [torch.empty_like(local) for _ in range(world)]
         dist.all_gather(parts, local.contiguous(), group=group)
         full = torch.cat(parts, dim=0)
+    if local.is_cuda:
+        torch.cuda.nvtx.range_pop()
     if all(s == mx for s in sizes):
         return full
     return torch.cat([full[r * mx: r * mx + sizes[r]] for r in range(world)], dim=0)
@@ -108,7 +112,9 @@ class FusedGatherQKANLayer:
             _b.check(_b.lib().qkan_layer_forward_peers(eng.handle(), xd.data_ptr(), xd.shape[0], ptrs, world, lo,
                                                        eng._stream_ptr()))
         if barrier:
+            torch.cuda.nvtx.range_push("qkan fused gather: symmetric-memory barrier")
             hdl.barrier()          # every rank's kernel has finished: all rows of all ranks are in place
+            torch.cuda.nvtx.range_pop()
         return out
 
 

@@ -117,9 +117,11 @@ typedef struct {
     int grid, smem_bytes;       /* of the most recent launch (0 before the first)                         */
     /* work per sample */
     int passes_survey, passes_exec;
-    int scaled_rotations;       /* 1: CHEB passes run in the scaled form Ry = gamma * M(t), one FMA per real output,
-                                   gamma^D and the quarter turns deferred to the last pass (block engine, compat
-                                   mode, 1 <= D <= 16); 0: plain (cos, sin) rotations                         */
+    int scaled_rotations;       /* form of the CHEB passes (block engine, compat mode, 1 <= D <= 16):
+                                   2: sin-weighted basis (u, s v): entry (c, 1 - c^2), no square root (D <= 8);
+                                   1: scaled form Ry = gamma * M(t), one FMA per real output, gamma^D and the
+                                      quarter turns deferred to the last pass;
+                                   0: plain (cos, sin) rotations (generic kernels)                            */
     int input_window;           /* > 0: window kernel (wide input rows) - rotation entries are built per row step
                                    from this many inputs instead of once per sample from all N                 */
     int element_owner;          /* 1: element-owner kernel (wide input rows) - the lanes of a row own its input elements: each

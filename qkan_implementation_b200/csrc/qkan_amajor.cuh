@@ -140,29 +140,69 @@ inline size_t amajor_smem_bytes(int N, int SPC, int row_bytes, int SU, int sub) 
 constexpr size_t AMAJOR_SMEM_CAP = 200 * 1024;
 
 // CHEB on one input element: the block state `init` through D applications of Ry(theta_x), cos(theta_x / 2) = c;
-// returns the f_x = 0 amplitudes of the two f_w halves.
-//   D >= 3: scaled form - D - 1 full passes M(t) (8 FMA), then the pruned pass alpha u + beta v with gamma^D and the
-//           quarter turns (4 MUL + 4 FMA); the conversion of c into (t, alpha, beta) costs one reciprocal square root and
-//           about 24 FP64 instructions + 14 selects per element;
-//   D <= 2: plain (cos, sin) rotations - D - 1 full passes (8 MUL + 8 FMA), then the pruned pass (4 MUL + 4 FMA); the
-//           conversion is one square root.  8 + 16 (D - 1) + 8 against 24 + 8 (D - 1) + 8
-//           FP64 instructions and no selects: measured faster at D = 1, 2 (N8 K8, 10 M: +4.5 %, +2 %), slower at D = 3 (-3.6 %; N4 K4 D3 -4 %): profiles/r02p_bench_cs_form_d3.json.
-constexpr int CS_FORM_MAX_DT = 2;
-constexpr bool cheb_uses_cs_form(int DT) { return DT <= CS_FORM_MAX_DT; }
+// returns the f_x = 0 amplitudes of the two f_w halves.  Two forms, chosen per compile-time degree:
+//
+//   sin-weighted basis (D <= SW_FORM_MAX_DT).  The f_x = 1 amplitude of every pair is stored multiplied by
+//       s = sin(theta_x / 2):  (u, w) = (amp[f_x = 0], s * amp[f_x = 1]).  In that basis Ry(theta_x) reads
+//           u' = c u - w,        w' = s^2 u + c w,        s^2 = 1 - c^2    (one FMA, exact to half an ulp)
+//       so the rotation entry is (c, s^2): no square root, no reciprocal, no case selection.  A full pass over a
+//       block is 4 MUL + 8 FMA (complex amplitudes, both f_w halves); the last pass, pruned to its f_x = 0 outputs,
+//       is 4 FMA - the post-selected amplitude is a u component, so the basis scale never has to be undone.  The
+//       prepared block state has no f_x = 1 component (PREPARE leaves f_x in |0>), so it is the same vector in this
+//       basis; BlockParams::init is read as stored amplitudes.  (A diagonal change of basis of the simulated state -
+//       the same device as deferring gamma^D in the scaled form or the 1/sqrt(2) of every Hadamard to the read-out.)
+//       Per element: 1 + 12 (D - 1) + 4 FP64 instructions.
+//   scaled form (D > SW_FORM_MAX_DT): D - 1 full passes M(t) (8 FMA), then the pruned pass alpha u + beta v with
+//       gamma^D and the quarter turns (4 MUL + 4 FMA); the conversion of c into (t, alpha, beta) costs one reciprocal
+//       square root and about 24 FP64 instructions + 14 selects per element: 24 + 8 (D - 1) + 8.
+// The plain (cos, sin) form of round 2's first session (D <= 2: one square root + 16 (D - 1) + 8) is superseded by the
+// sin-weighted basis at every degree (profiles/r02p_bench_cs_form_d3.json has its measurements).
+#ifndef QKAN_SW_FORM_MAX_DT
+#define QKAN_SW_FORM_MAX_DT 8
+#endif
+constexpr int SW_FORM_MAX_DT = QKAN_SW_FORM_MAX_DT;
+constexpr bool cheb_uses_sw_form(int DT) { return DT <= SW_FORM_MAX_DT; }
+
+// one full pass in the sin-weighted basis: (u, w) <- (c u - w, s2 u + c w)
+template <typename R> QK_HD void rot_sw(Cplx<R>& u, Cplx<R>& w, R c, R s2) {
+    const R ur = u.re, ui = u.im;
+    u.re = qk_fma(c, ur, -w.re);
+    u.im = qk_fma(c, ui, -w.im);
+    w.re = qk_fma(s2, ur, c * w.re);
+    w.im = qk_fma(s2, ui, c * w.im);
+}
+template <typename R> QK_HD void rot_sw(Real<R>& u, Real<R>& w, R c, R s2) {
+    const R ur = u.re;
+    u.re = qk_fma(c, ur, -w.re);
+    w.re = qk_fma(s2, ur, c * w.re);
+}
+// its f_x = 0 output only: c u - w
+template <typename R> QK_HD Cplx<R> rot_sw_lo(const Cplx<R>& u, const Cplx<R>& w, R c) {
+    Cplx<R> o;
+    o.re = qk_fma(c, u.re, -w.re);
+    o.im = qk_fma(c, u.im, -w.im);
+    return o;
+}
+template <typename R> QK_HD Real<R> rot_sw_lo(const Real<R>& u, const Real<R>& w, R c) {
+    Real<R> o;
+    o.re = qk_fma(c, u.re, -w.re);
+    return o;
+}
+
 template <class A, typename R, int DT>
 QK_HD void cheb_element(const A (&init)[4], R c, A& lo0, A& lo2) {
     A v[4];
     QK_UNROLL
     for (int q = 0; q < 4; ++q) v[q] = init[q];
-    if constexpr (cheb_uses_cs_form(DT)) {
-        const R s = qk_sqrt((R(1) - c) * (R(1) + c));
+    if constexpr (cheb_uses_sw_form(DT)) {
+        const R s2 = qk_fma(-c, c, R(1));
         QK_UNROLL
         for (int r = 0; r + 1 < DT; ++r) {
-            rot(v[0], v[1], c, s);
-            rot(v[2], v[3], c, s);
+            rot_sw(v[0], v[1], c, s2);
+            rot_sw(v[2], v[3], c, s2);
         }
-        lo0 = rot_lo(v[0], v[1], c, s);
-        lo2 = rot_lo(v[2], v[3], c, s);
+        lo0 = rot_sw_lo(v[0], v[1], c);
+        lo2 = rot_sw_lo(v[2], v[3], c);
     } else {
         const TanEntry<R> e = tan_entry<R>(c, DT);
         QK_UNROLL

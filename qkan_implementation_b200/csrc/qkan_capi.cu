@@ -722,10 +722,11 @@ extern "C" int qkan_layer_info(qkan_layer* l, qkan_kernel_info* info) {
             }
             info->degree_factored = 1;
             info->cheb_elements = (int)elems;
-            if (cheb_uses_cs_form(l->D)) {                    // plain (cos, sin) rotations below four applications
-                info->scaled_rotations = 0;
-                info->flops_exec = cf * (elems * (24.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
-                info->fp_inst_exec = cf * (elems * (16.0 * (Dd - 1.0) + 8.0) + 4.0 * (double)info->blocks);
+            if (cheb_uses_sw_form(l->D)) {
+                // sin-weighted basis: s^2 (1 FMA), D - 1 full passes (4 MUL + 8 FMA), the pruned pass (4 FMA)
+                info->scaled_rotations = 2;
+                info->flops_exec = cf * (elems * (20.0 * (Dd - 1.0) + 8.0 + 2.0) + 8.0 * (double)info->blocks);
+                info->fp_inst_exec = cf * (elems * (12.0 * (Dd - 1.0) + 4.0 + 1.0) + 4.0 * (double)info->blocks);
             } else {
                 info->flops_exec = cf * (elems * (16.0 * (Dd - 1.0) + 12.0) + 8.0 * (double)info->blocks);
                 info->fp_inst_exec = cf * (elems * 8.0 * Dd + 4.0 * (double)info->blocks);

@@ -196,7 +196,7 @@ def test_wide_input_rows(Q, N, K, D):
         layer = Q.QKANLayer(N, K, D, dtype=dtype)
         y, a = layer.forward(x, W, return_amplitudes=True)
         info = layer.kernel_info()
-        assert info["degree_factored"] == 1 and info["element_owner"] == 1 and info["scaled_rotations"] == (1 if D >= 3 else 0), info
+        assert info["degree_factored"] == 1 and info["element_owner"] == 1 and info["scaled_rotations"] == (2 if D <= 8 else 1), info
         assert_close(y, ref, dtype)
         layer.forward(torch.from_numpy(x).cuda(), W)       # device input: the count stays for the caller
         assert layer.out_of_range_count() == n_bad         # an input shared by two windows is counted once
@@ -302,17 +302,17 @@ def test_c_abi_direct(Q):
     info = b.KernelInfo()
     assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
     assert info.qubits == 8 and info.flops_survey == 21504 and info.grid > 0
-    # per (a, b): one evolution through CHEB (2 full passes of 8 FMA + the pruned pass, 4 MUL + 4 FMA), then SELECT on
-    # each of the D + 1 degree copies (4 FMA)
-    assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 1 and info.degree_factored == 1
+    # CHEB once per evaluated input element, in the sin-weighted basis (D <= 8): s^2 (1 FMA), 2 full passes of
+    # 4 MUL + 8 FMA, the pruned pass (4 FMA); SELECT on each of the D + 1 degree copies of every (a, b) (4 FMA)
+    assert info.engine == 0 and info.blocks == 64 and info.scaled_rotations == 2 and info.degree_factored == 1
     assert info.direct_rows == 1 and info.cheb_elements == 4
-    # CHEB once per evaluated input element (2 full passes of 8 FMA + the pruned pass, 4 MUL + 4 FMA), SELECT per block (4 FMA)
-    assert info.flops_exec == 4 * (16 * 2 + 12) + 64 * 8 and info.fp_inst_exec == 4 * 8 * 3 + 64 * 4
-    h2 = ctypes.c_void_p()                                   # D <= 2: plain (cos, sin) rotations per element
-    assert lib.qkan_layer_create(ctypes.byref(h2), 8, 8, 2, 0, 0, 1, 0) == 0
+    assert info.flops_exec == 4 * (20 * 2 + 8 + 2) + 64 * 8 and info.fp_inst_exec == 4 * (12 * 2 + 4 + 1) + 64 * 4
+    h2 = ctypes.c_void_p()                                   # D > 8: scaled form Ry = gamma M(t)
+    assert lib.qkan_layer_create(ctypes.byref(h2), 8, 8, 12, 0, 0, 1, 0) == 0
     assert lib.qkan_layer_info(h2, ctypes.byref(info)) == 0
-    assert info.scaled_rotations == 0 and info.flops_exec == 8 * (24 + 12) + 192 * 8 and info.fp_inst_exec == 8 * (16 + 8) + 192 * 4
+    assert info.scaled_rotations == 1 and info.flops_exec == 8 * (16 * 11 + 12) + 8 * 8 * 13 * 8 and info.fp_inst_exec == 8 * 8 * 12 + 8 * 8 * 13 * 4
     lib.qkan_layer_destroy(h2)
+    assert lib.qkan_layer_info(h, ctypes.byref(info)) == 0
     assert info.flops_per_block_basis == 64 * (16 * 3 + 4)
     lib.qkan_layer_destroy(h)
     assert b.measure_fma_peak(0, True) > 5.0

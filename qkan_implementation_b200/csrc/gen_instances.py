@@ -105,7 +105,8 @@ AMAJOR = {
 # (profiles/r02e_tune_direct.jsonl, r02d_tune_direct_all.jsonl)
 DIRECT = {
     (4, 256): [(2, 1)],
-    (2, 256): [(3, 0)],      # tuning variant (complex128 only)
+    (2, 256): [(3, 0)],      # tuning variant (complex128 only); (4, 128) x 4 CTAs and (2, 128) x 6 CTAs measured equal / slower
+                             # with the compile-time-G kernels too (profiles/r02u_tune_direct.jsonl)
 }
 # element-owner kernels (wide input rows): (SU, NT) -> [(MINB, is_default)]
 ELEM = {

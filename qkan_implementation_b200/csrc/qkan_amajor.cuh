@@ -323,6 +323,11 @@ QK_HD void fill_elem_step(long long step, const double* W, int N, int K, int D, 
 }
 
 #if defined(__CUDACC__)
+// |v| >= 1, infinite or NaN, decided on the high word alone (one LOP3 + one ISETP on the integer pipe; the FP64 pipe is the
+// scarce one).  Inputs strictly inside (-1, 1) - all of a normalised batch - need neither the clip nor the range count
+// (ChebyshevStep.py:46-52); the rare others take the exact path.
+__device__ __forceinline__ bool at_or_beyond_unit(double v) { return (__double2hiint(v) & 0x7fffffff) >= 0x3ff00000; }
+
 // result store.  plain: one local buffer, no amplitudes (a single uniform branch in the hot path)
 template <class A, typename R>
 __device__ __forceinline__ void amajor_store(const BlockParams& p, const A& acc, double* __restrict__ out_t, void* amps_t, int o) {
@@ -458,10 +463,13 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
             int n = pre_n0;
             char* dst = pre_dst0;
             for (int e = tid; e < n_in; e += NT) {
-                const double v = xs[e];
-                if (!(fabs(v) <= 1.0 + 1e-8)) ++bad;
+                double v = xs[e];
+                if (at_or_beyond_unit(v)) {                   // |v| >= 1 or NaN: the exact test and the clip
+                    if (!(fabs(v) <= 1.0 + 1e-8)) ++bad;
+                    v = (double)clip_unit<double>(v);
+                }
                 A lo0, lo2;
-                cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0, lo2);
+                cheb_element<A, R, DT>(init, (R)v, lo0, lo2);
                 *reinterpret_cast<A*>(dst) = lo0;
                 *reinterpret_cast<A*>(dst + plane) = lo2;
                 n += pre_dn;
@@ -537,13 +545,16 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_amajor_kernel(const Block
 // its row's N (D + 1) blocks - no shared memory, no barriers, no tiles; SU samples per lane share the SELECT
 // entries, and the next chunk's inputs are loaded while the current one is evaluated.  An element read by K / N
 // rows is evaluated by each of them (K evaluations per sample instead of N).
-template <class A, typename R, int SU, int NT, int MINB, int DT>
+// GL >= 0: the lanes per sample G = 2^GL are a compile-time constant, so the SELECT loads of a block row are one base
+// register + immediate offsets (the run-time-G kernel spent 21 integer instructions per 8 table loads on addresses).
+template <class A, typename R, int SU, int NT, int MINB, int DT, int GL>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const BlockParams p) {
     constexpr int D1 = DT + 1;
-    const int G = p.G, SPC = p.SPC;
+    const int G = GL >= 0 ? (1 << GL) : p.G;
+    const int SPC = GL >= 0 ? (NT >> GL) : p.SPC;
     const int tid = threadIdx.x;
     const int k = tid & (G - 1);                             // the lane's output row
-    const int slot = tid >> p.g_k_log2;                      // sample slot inside the CTA
+    const int slot = GL >= 0 ? (tid >> GL) : (tid >> p.g_k_log2);   // sample slot inside the CTA
     if (k >= p.K) return;                                    // no cross-lane step in this kernel: idle lanes leave
     const int nk = (int)(((long long)k * p.N) / p.K);        // the row's input element (ChebyshevStep.py:64, QKANLayer.py:132)
     const bool counts = ((long long)k * p.N) % p.K == 0;     // the first row that reads an element reports its range violation
@@ -591,12 +602,22 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const Block
         }
         const bool full = left > (long long)(SU - 1) * SPC;   // every sample of the lane's share exists
         A lo0[SU], lo2[SU], acc[SU];
+        // range count (the reference prints a warning, ChebyshevStep.py:46-49) and clip (:52): only inputs with |v| >= 1
+        // (or NaN) can need either
+        bool edge = false;
+        QK_UNROLL
+        for (int j = 0; j < SU; ++j) edge |= at_or_beyond_unit(xv[j]);
+        if (edge) {
+            QK_UNROLL
+            for (int j = 0; j < SU; ++j) {
+                const double v = xv[j];
+                if (!(fabs(v) <= 1.0 + 1e-8) && counts && (full || (long long)j * SPC < left)) ++bad;
+                xv[j] = (double)clip_unit<double>(v);
+            }
+        }
         QK_UNROLL
         for (int j = 0; j < SU; ++j) {
-            // range count (the reference prints a warning, ChebyshevStep.py:46-49), clip (:52), CHEB sequence of the element
-            const double v = xv[j];
-            if (!(fabs(v) <= 1.0 + 1e-8) && counts && (full || (long long)j * SPC < left)) ++bad;
-            cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
+            cheb_element<A, R, DT>(init, (R)xv[j], lo0[j], lo2[j]);      // CHEB sequence of the element
             set_amp(acc[j], 0.0);
         }
         // SELECT on the row's N (D + 1) blocks; UNPREPARE + SUM + post-selection is the lane's running sum
@@ -626,15 +647,19 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_direct_kernel(const Block
 // Element-owner kernel (see ElemLayout above): no shared memory, SU samples per lane, x read straight from global memory
 // (the G_r lanes of a row read G_r consecutive inputs), the next element's inputs in flight during the current element's
 // arithmetic.  An input shared by two rows (window boundaries) is evaluated by both.
-template <class A, typename R, int SU, int NT, int MINB, int DT>
+// GL >= 0: rows one after the other (G_k = 1) with G = G_r = 2^GL lanes per row as compile-time constants (immediate
+// offsets for the SELECT loads, unrolled butterfly).
+template <class A, typename R, int SU, int NT, int MINB, int DT, int GL>
 __global__ void __launch_bounds__(NT, MINB) qkan_block_elem_kernel(const BlockParams p) {
     constexpr int D1 = DT + 1;
-    const int G = p.G, G_r = p.G_r, SPC = p.SPC;
+    const int G = GL >= 0 ? (1 << GL) : p.G;
+    const int G_r = GL >= 0 ? (1 << GL) : p.G_r;
+    const int SPC = GL >= 0 ? (NT >> GL) : p.SPC;
     const int tid = threadIdx.x;
     const int g = tid & (G - 1);
     const int r = g & (G_r - 1);
-    const int k = g >> p.g_r_log2;
-    const int slot = tid >> (p.g_r_log2 + p.g_k_log2);
+    const int k = GL >= 0 ? 0 : (g >> p.g_r_log2);
+    const int slot = GL >= 0 ? (tid >> GL) : (tid >> (p.g_r_log2 + p.g_k_log2));
     const CS<R>* __restrict__ we = reinterpret_cast<const CS<R>*>(p.cstab);
     const int* __restrict__ xe = p.xotab;
 
@@ -680,20 +705,28 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_elem_kernel(const BlockPa
                 }
                 A lo0[SU], lo2[SU];
                 const bool counts = e_cur >= 0 && (e_cur & (1 << 30));
+                // range count (ChebyshevStep.py:46-49; once per input) and clip (:52): only for |v| >= 1 or NaN
+                bool edge = false;
                 QK_UNROLL
-                for (int j = 0; j < SU; ++j) {
-                    // range count (ChebyshevStep.py:46-49; once per input), clip (:52), CHEB sequence of the element
-                    const double v = xv[j];
-                    if (counts && (long long)j * SPC < left && !(fabs(v) <= 1.0 + 1e-8)) ++bad;
-                    cheb_element<A, R, DT>(init, clip_unit<R>(v), lo0[j], lo2[j]);
+                for (int j = 0; j < SU; ++j) edge |= at_or_beyond_unit(xv[j]);
+                if (edge) {
+                    QK_UNROLL
+                    for (int j = 0; j < SU; ++j) {
+                        const double v = xv[j];
+                        if (counts && (long long)j * SPC < left && !(fabs(v) <= 1.0 + 1e-8)) ++bad;
+                        xv[j] = (double)clip_unit<double>(v);
+                    }
                 }
+                QK_UNROLL
+                for (int j = 0; j < SU; ++j) cheb_element<A, R, DT>(init, (R)xv[j], lo0[j], lo2[j]);   // CHEB sequence of the element
                 // SELECT on the element's K (D + 1) blocks (padding entries rotate by pi: they add exactly 0)
                 for (int j = 0; j < p.K; ++j, wp += jstep) select_blocks<A, R, SU, DT>(lo0, lo2, wp, G, acc);
             }
             // UNPREPARE + SUM + post-selection: the sum over the row's blocks, finished across the G_r lanes
-            const int b = (bi << p.g_k_log2) + k;
+            const int b = GL >= 0 ? bi : ((bi << p.g_k_log2) + k);
             QK_UNROLL
             for (int j = 0; j < SU; ++j) {
+                QK_UNROLL
                 for (int m = G_r >> 1; m >= 1; m >>= 1) add_amp(acc[j], shfl_xor_amp(acc[j], m));
                 if (r == 0 && b < p.K && (long long)j * SPC < left) {
                     const long long o = (s0 + (long long)j * SPC) * p.K + b;
@@ -725,10 +758,9 @@ __global__ void qkan_prepare_elem_tables_kernel(const double* W, int N, int K, i
     fill_elem_step<R>(step, W, N, K, D, passes, brows, g_r_log2, g_k_log2, we, xe);
 }
 
-template <class A, typename R, int SU, int NT, int MINB, int DT>
-cudaError_t launch_elem(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    if (p0.D != DT) return cudaErrorInvalidValue;
-    auto kern = qkan_block_elem_kernel<A, R, SU, NT, MINB, DT>;
+template <class A, typename R, int SU, int NT, int MINB, int DT, int GL>
+cudaError_t launch_elem_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    auto kern = qkan_block_elem_kernel<A, R, SU, NT, MINB, DT, GL>;
     BlockParams p = p0;
     const int SPC = NT / G;
     int per_sm = 0;
@@ -748,6 +780,15 @@ cudaError_t launch_elem(const BlockParams& p0, int G, int sm_count, cudaStream_t
     if (smem_out) *smem_out = 0;
     kern<<<(unsigned)grid, NT, 0, stream>>>(p);
     return cudaGetLastError();
+}
+// 16 lanes per row (every row wider than ~14 inputs: plan_elem_layout) is compiled in; other splits run the run-time-G kernel
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+cudaError_t launch_elem(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p0.D != DT) return cudaErrorInvalidValue;
+    static const bool generic_only = getenv("QKAN_ELEM_RUNTIME_G") != nullptr;        // A/B aid
+    if (!generic_only && p0.g_k_log2 == 0 && p0.g_r_log2 == 4 && G == 16)
+        return launch_elem_impl<A, R, SU, NT, MINB, DT, 4>(p0, G, sm_count, stream, grid_out, smem_out);
+    return launch_elem_impl<A, R, SU, NT, MINB, DT, -1>(p0, G, sm_count, stream, grid_out, smem_out);
 }
 template <class A, typename R, int SU, int NT, int MINB, int DT>
 BlockKernelInfo make_elem_info(int is_default) {
@@ -848,10 +889,9 @@ BlockKernelInfo make_amajor_info(int is_default) {
     return k;
 }
 
-template <class A, typename R, int SU, int NT, int MINB, int DT>
-cudaError_t launch_direct(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
-    if (p0.D != DT || p0.g_r_log2 != 0 || p0.brows != 1 || p0.K % p0.N != 0) return cudaErrorInvalidValue;
-    auto kern = qkan_block_direct_kernel<A, R, SU, NT, MINB, DT>;
+template <class A, typename R, int SU, int NT, int MINB, int DT, int GL>
+cudaError_t launch_direct_impl(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    auto kern = qkan_block_direct_kernel<A, R, SU, NT, MINB, DT, GL>;
     BlockParams p = p0;
     const int SPC = NT / G;
     int per_sm = 0;
@@ -871,6 +911,21 @@ cudaError_t launch_direct(const BlockParams& p0, int G, int sm_count, cudaStream
     if (smem_out) *smem_out = 0;
     kern<<<(unsigned)grid, NT, 0, stream>>>(p);
     return cudaGetLastError();
+}
+// G = 4, 8, 16 lanes per sample (K of the BASELINE layers) are compiled in; any other power of two runs the run-time-G kernel
+template <class A, typename R, int SU, int NT, int MINB, int DT>
+cudaError_t launch_direct(const BlockParams& p0, int G, int sm_count, cudaStream_t stream, int* grid_out, int* smem_out) {
+    if (p0.D != DT || p0.g_r_log2 != 0 || p0.brows != 1 || p0.K % p0.N != 0 || G != (1 << p0.g_k_log2)) return cudaErrorInvalidValue;
+    static const bool generic_only = getenv("QKAN_DIRECT_RUNTIME_G") != nullptr;      // A/B aid
+    if (!generic_only) {
+        switch (p0.g_k_log2) {
+            case 2: return launch_direct_impl<A, R, SU, NT, MINB, DT, 2>(p0, G, sm_count, stream, grid_out, smem_out);
+            case 3: return launch_direct_impl<A, R, SU, NT, MINB, DT, 3>(p0, G, sm_count, stream, grid_out, smem_out);
+            case 4: return launch_direct_impl<A, R, SU, NT, MINB, DT, 4>(p0, G, sm_count, stream, grid_out, smem_out);
+            default: break;
+        }
+    }
+    return launch_direct_impl<A, R, SU, NT, MINB, DT, -1>(p0, G, sm_count, stream, grid_out, smem_out);
 }
 template <class A, typename R, int SU, int NT, int MINB, int DT>
 BlockKernelInfo make_direct_info(int is_default) {

@@ -552,21 +552,49 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
         CU(cudaStreamSynchronize(l->s_k));
         return QKAN_OK;
     }
-    // chunks: enough to overlap copy-in / compute / copy-out, each a multiple of the CTA tile.  About 8 MiB of traffic per
-    // chunk (8 chunks for 1M x (4 in + 4 out) doubles): the first copy-in is not overlapped, so fewer chunks expose the
-    // fill, while each DMA copy carries ~10 us of fixed cost, so many small chunks are slower (16: +9 %, 64: +60 %)
-    int nchunk = (int)((B * (int64_t)(l->N + l->K) * 8) >> 23);
-    if (const char* e = getenv("QKAN_HOST_CHUNKS")) nchunk = atoi(e);   // tuning aid
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > MAX_CHUNKS) nchunk = MAX_CHUNKS;
-    int64_t per = (B + nchunk - 1) / nchunk;
+    // chunks: enough to overlap copy-in / compute / copy-out.  About 8 MiB of traffic per chunk but at most 16 chunks (each
+    // DMA copy carries ~10 us of fixed cost: N4 K4, 1M samples: 8 chunks 0.84 ms, 16 +9 %, 64 +60 %; N16 K16, 256 MB: 8 or 16
+    // chunks 3.13 ms, 32 chunks 3.26 ms), and never less than one full wave of the forward kernel (a chunk's kernel takes
+    // the time of one CTA chunk however few CTAs it has: N784 K10 D5 cut into 64 chunks of 1 562 samples ran 17.2 ms against
+    // 11.8 ms with 8), a multiple of the CTA tile.  Making the first and the last chunk smaller (QKAN_HOST_EDGE_DIV > 1;
+    // nothing overlaps the first copy-in and the last result write) measured no better: profiles/r02v_e2e_ab.txt.
     const int64_t spi = l->engine == 0 ? (l->bkern->NT >> (l->lay.g_r_log2 + l->lay.g_k_log2)) : l->kern->spi;
+    const int64_t wave = l->engine == 0 ? (int64_t)l->sm_count * 2 * spi * (l->bkern->SU > 0 ? l->bkern->SU : 1) : spi;
+    int64_t per = ((int64_t)8 << 20) / ((int64_t)(l->N + l->K) * 8);
+    if (const char* e = getenv("QKAN_HOST_CHUNKS")) {        // tuning aid: this many uniform-size chunks
+        const int nc = atoi(e);
+        if (nc >= 1) per = (B + nc - 1) / nc;
+    } else {
+        if (per * 16 < B) per = (B + 15) / 16;
+        if (per < wave) per = wave;
+    }
+    if (per * MAX_CHUNKS < B) per = (B + MAX_CHUNKS - 1) / MAX_CHUNKS;
     per = (per + spi - 1) / spi * spi;
+    int edge_div = 1;
+    if (const char* e = getenv("QKAN_HOST_EDGE_DIV")) edge_div = atoi(e);
+    int64_t cut[MAX_CHUNKS + 3];
+    int nchunk = 0;
+    cut[0] = 0;
+    {
+        int64_t edge = edge_div > 1 ? (per / edge_div + spi - 1) / spi * spi : 0;
+        if (edge < spi || 2 * edge + per > B) edge = 0;       // too small a batch for edges
+        int64_t mid = B - 2 * edge;
+        int nmid = (int)((mid + per - 1) / per);
+        if (nmid < 1) nmid = 1;
+        if (nmid > MAX_CHUNKS - 2) nmid = MAX_CHUNKS - 2;
+        int64_t mper = ((mid + nmid - 1) / nmid + spi - 1) / spi * spi;
+        if (edge) cut[++nchunk] = edge;
+        for (int i = 0; i < nmid; ++i) {
+            int64_t hi = cut[nchunk] + mper;
+            if (hi > B - edge || i == nmid - 1) hi = B - edge;
+            if (hi > cut[nchunk]) cut[++nchunk] = hi;
+        }
+        if (edge) cut[++nchunk] = B;
+    }
     const size_t asz = 2 * amp_real_size(l->dtype);
     auto enqueue = [&]() -> int {
-        int i = 0;
-        for (int64_t off = 0; off < B; off += per, ++i) {
-            const int64_t n = (B - off < per) ? (B - off) : per;
+        for (int i = 0; i < nchunk; ++i) {
+            const int64_t off = cut[i], n = cut[i + 1] - cut[i];
             const double* xin = (const double*)dx + off * l->N;
             if (!in_direct) {
                 CU(cudaMemcpyAsync(l->d_x + off * l->N, x + off * l->N, (size_t)n * l->N * sizeof(double),
@@ -594,7 +622,7 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     };
     // CUDA graph of the pipeline: built on the second consecutive call with the same buffers, replayed afterwards.
     // Pinned buffers only (copies from pageable memory are staged by the driver and cannot be captured usefully).
-    const qkan_layer::HostKey key{x, out, amps, B, in_direct ? 1 : 0, out_direct ? 1 : 0, nchunk};
+    const qkan_layer::HostKey key{x, out, amps, B, in_direct ? 1 : 0, out_direct ? 1 : 0, nchunk * 64 + (edge_div & 63)};
     auto same = [](const qkan_layer::HostKey& a, const qkan_layer::HostKey& b) {
         return a.x == b.x && a.out == b.out && a.amps == b.amps && a.B == b.B && a.in_direct == b.in_direct &&
                a.out_direct == b.out_direct && a.nchunk == b.nchunk;

@@ -20,8 +20,10 @@ oh = torch.empty((B, K), dtype=torch.float64).pin_memory()
 xn, on = xh.numpy(), oh.numpy()
 layer = QKANLayer(N, K, D)
 ref = layer.forward(x.cuda(), W).cpu().numpy()
-for mode, chunks, graph in (("zero_copy", 0, 1), ("staged", 4, 0), ("staged", 4, 1), ("staged", 8, 1), ("staged", 0, 1), ("staged", 32, 1), ("staged", 64, 1),
-                            ("copy_in", 4, 0), ("copy_in", 8, 1), ("copy_in", 0, 1), ("copy_in", 32, 1), ("copy_out", 0, 1), ("zero_copy", 0, 1)):
+for mode, chunks, graph, edge in (("zero_copy", 0, 1, 4), ("staged", 4, 0, 1), ("staged", 8, 1, 1), ("staged", 0, 1, 1), ("staged", 0, 1, 4), ("staged", 32, 1, 1),
+                                  ("copy_in", 4, 0, 1), ("copy_in", 8, 1, 1), ("copy_in", 8, 1, 4), ("copy_in", 0, 1, 1), ("copy_in", 0, 1, 2), ("copy_in", 0, 1, 4),
+                                  ("copy_in", 0, 1, 8), ("copy_in", 16, 1, 4), ("copy_in", 0, 0, 4), ("copy_out", 0, 1, 4), ("zero_copy", 0, 1, 4)):
+    os.environ["QKAN_HOST_EDGE_DIV"] = str(edge)
     if graph:
         os.environ.pop("QKAN_HOST_NO_GRAPH", None)
     else:
@@ -41,8 +43,9 @@ for mode, chunks, graph in (("zero_copy", 0, 1), ("staged", 4, 0), ("staged", 4,
         layer.forward(xn, W, out=on, check_range=False)
         ts.append(time.perf_counter() - t0)
     ms = float(np.median(ts)) * 1e3
-    print(f"{mode:10s} chunks={chunks or 'auto':>4} graph={graph} N={N} K={K} D={D} B={B}: {ms:.3f} ms  {B / ms / 1e6:.3f} Gsamples/s  {(N + K) * 8 * B / ms / 1e6:.1f} GB/s both ways")
+    print(f"{mode:10s} chunks={chunks or 'auto':>4} edge_div={edge} graph={graph} N={N} K={K} D={D} B={B}: {ms:.3f} ms  {B / ms / 1e6:.3f} Gsamples/s  {(N + K) * 8 * B / ms / 1e6:.1f} GB/s both ways")
 os.environ.pop("QKAN_HOST_PATH", None)
+os.environ.pop("QKAN_HOST_EDGE_DIV", None)
 os.environ.pop("QKAN_HOST_CHUNKS", None)
 os.environ.pop("QKAN_HOST_NO_GRAPH", None)
 # pageable numpy buffers always take the staged path

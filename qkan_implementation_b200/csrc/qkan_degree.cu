@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -147,7 +148,12 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
     };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;      // the warp's 32 x 32 quadrant
+    // the warp's 32 x 32 quadrant, rotated from CTA to CTA: warp w of every resident CTA sits on SM sub-partition w, and the
+    // strictly lower quadrant of a diagonal tile (the transpose of the upper one) is not computed - without the rotation
+    // one sub-partition's tensor pipe would get all the idle warps
+    const int quad = (warp + blockIdx.x + blockIdx.y) & 3;
+    const int wm = (quad & 1) * 32, wn = (quad >> 1) * 32;
+    const bool idle = diag && wm > wn;
     const int lr = lane >> 2, lk = lane & 3;
     double acc[4][4][2];
 #pragma unroll
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
             if (!diag) prefetch(s0 + KC, xb, fb_lo, nfb);
         }
         const double* Bsrc = diag ? As : Bs;
+        if (idle) continue;
 #pragma unroll
         for (int k4 = 0; k4 < KC; k4 += 4) {
             double a[4], b[4];
@@ -197,23 +204,34 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
         }
 }
 
-// sum the slices in a fixed order and scatter the tile into the degree-major (P+1) x (P+1) result (both triangles)
-__global__ void qkan_cheb_gram_reduce_kernel(const double* partial, int n_tiles, int S, int T, int F, int D, int P, double* G) {
+// sum the slices in a fixed order and scatter the tile into the degree-major (P+1) x (P+1) result (both triangles).
+// grid (tiles, TILE * TILE / blockDim): one element per thread, the slices read as coalesced 2 KB rows (a 15-CTA version that
+// walked a whole tile per CTA took 0.4 ms of the 4.07 ms Gram step).  Diagonal tiles contribute their upper triangle only
+// (the Gram kernel does not compute their strictly lower quadrant).
+__global__ void __launch_bounds__(256) qkan_cheb_gram_reduce_kernel(const double* __restrict__ partial, int n_tiles, int S, int T, int F, int D, int P,
+                                                                     double* __restrict__ G) {
     const int tile = blockIdx.x;
     int ti = 0, rem = tile;
     while (rem >= T - ti) { rem -= T - ti; ++ti; }
     const int tj = ti + rem;
     const int D1 = D + 1;
     auto to_degree_major = [&](int c) { return c == P ? P : (c % D1) * F + c / D1; };
-    for (int e = threadIdx.x; e < TILE * TILE; e += blockDim.x) {
-        const int r = ti * TILE + e / TILE, c = tj * TILE + e % TILE;
-        if (r > P || c > P) continue;
-        double s = 0.0;
-        for (int q = 0; q < S; ++q) s += partial[((size_t)q * n_tiles + tile) * (TILE * TILE) + e];
-        const int rr = to_degree_major(r), cc = to_degree_major(c);
-        G[(size_t)rr * (P + 1) + cc] = s;
-        G[(size_t)cc * (P + 1) + rr] = s;
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    const int r = ti * TILE + e / TILE, c = tj * TILE + e % TILE;
+    if (r > P || c > P || (ti == tj && r > c)) return;
+    const double* src = partial + (size_t)tile * (TILE * TILE) + e;
+    const size_t stride = (size_t)n_tiles * (TILE * TILE);
+    double s = 0.0;
+    int q = 0;
+    for (; q + 4 <= S; q += 4) {                             // four loads in flight; the order of the additions is fixed
+        const double v0 = src[(size_t)q * stride], v1 = src[(size_t)(q + 1) * stride];
+        const double v2 = src[(size_t)(q + 2) * stride], v3 = src[(size_t)(q + 3) * stride];
+        s += v0; s += v1; s += v2; s += v3;
     }
+    for (; q < S; ++q) s += src[(size_t)q * stride];
+    const int rr = to_degree_major(r), cc = to_degree_major(c);
+    G[(size_t)rr * (P + 1) + cc] = s;
+    G[(size_t)cc * (P + 1) + rr] = s;
 }
 
 // ---- residual pass: one warp per sample, lanes over features
@@ -404,8 +422,13 @@ extern "C" int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes,
     const int P = F * (D + 1), T = (P + 1 + TILE - 1) / TILE, n_tiles = T * (T + 1) / 2;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // about four waves of CTAs, at least 8 chunks of samples per slice
-    int S = (4 * 4 * sms + n_tiles - 1) / n_tiles;
+    // eight whole waves of CTAs and not one CTA more (rounding up - 2 370 CTAs on 2 368 resident slots at 774 456 x 79,
+    // D = 3 - left the SMs idle 15 % of the kernel while two stragglers ran a fifth wave; 4 waves 3.68 ms, 6: 3.55, 8: 3.49,
+    // 12: 3.49), at least 8 chunks of samples per slice
+    const int per_sm = D >= 3 ? 4 : (D >= 1 ? 3 : 2);        // the launch bounds of qkan_cheb_gram_kernel<MAXI, .>
+    int waves = 8;
+    if (const char* e = getenv("QKAN_GRAM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;   // tuning aid
+    int S = waves * per_sm * sms / n_tiles;
     const long long max_s = n / (8 * KC) > 0 ? n / (8 * KC) : 1;
     if (S > max_s) S = (int)max_s;
     if (S < 1) S = 1;
@@ -440,7 +463,7 @@ extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");
-    qkan_cheb_gram_reduce_kernel<<<n_tiles, 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);
+    qkan_cheb_gram_reduce_kernel<<<dim3(n_tiles, TILE * TILE / 256), 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_reduce_kernel launch");
     return QKAN_OK;

@@ -104,6 +104,10 @@ __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, lon
     }
 }
 
+// Rejected variants (correct, A/B on one box, profiles/README.md): double-buffered chunks with one barrier (round 1),
+// a producer warp + mbarrier ring, cp.async input staging (round 2, first session), and chunks double buffered with the
+// production of chunk i + 1 sliced between the eight DMMA groups of chunk i (3 CTAs per SM: 3.55 ms against 3.49 ms);
+// 5 CTAs per SM at 96 registers (164 bytes spilled): 3.93 ms.
 // MAXI = most feature slots a thread fills per chunk and side: (64 / (D+1) + 2 features + the y slot) / 4
 template <int MAXI, int D1T>
 __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
@@ -425,7 +429,7 @@ extern "C" int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes,
     // eight whole waves of CTAs and not one CTA more (rounding up - 2 370 CTAs on 2 368 resident slots at 774 456 x 79,
     // D = 3 - left the SMs idle 15 % of the kernel while two stragglers ran a fifth wave; 4 waves 3.68 ms, 6: 3.55, 8: 3.49,
     // 12: 3.49), at least 8 chunks of samples per slice
-    const int per_sm = D >= 3 ? 4 : (D >= 1 ? 3 : 2);        // the launch bounds of qkan_cheb_gram_kernel<MAXI, .>
+    const int per_sm = D >= 3 ? 4 : (D >= 1 ? 3 : 2);   // the launch bounds of qkan_cheb_gram_kernel<MAXI, .>
     int waves = 8;
     if (const char* e = getenv("QKAN_GRAM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;   // tuning aid
     int S = waves * per_sm * sms / n_tiles;

@@ -104,15 +104,15 @@ AMAJOR = {
 # measured best on every BASELINE shape: four samples per lane, 256-thread CTAs, two CTAs per SM
 # (profiles/r02e_tune_direct.jsonl, r02d_tune_direct_all.jsonl)
 DIRECT = {
-    (4, 256): [(2, 1)],
-    (2, 256): [(3, 0)],      # tuning variant (complex128 only); (4, 128) x 4 CTAs and (2, 128) x 6 CTAs measured equal / slower
-                             # with the compile-time-G kernels too (profiles/r02u_tune_direct.jsonl)
+    (4, 256): [(2, 1)],      # (2, 256) x 3 CTAs, (4, 128) x 4 and (2, 128) x 6 measured equal or slower, with run-time and with
+                             # compile-time lanes per sample (profiles/r02e_tune_direct.jsonl, r02u_tune_direct.jsonl): not built
 }
-# element-owner kernels (wide input rows): (SU, NT) -> [(MINB, is_default)]
+# complex64 (half the registers per sample): (4, 256) x 3 or 4 CTAs and (8, 256) x 2 or 3 CTAs measured within noise of / slower than
+# the default on every BASELINE shape (profiles/r02y_tune_c64.jsonl): not built
+DIRECT_EXTRA = {}
+# element-owner kernels (wide input rows): (SU, NT) -> [(MINB, is_default)]; no shared memory, so four samples per lane always launch
 ELEM = {
     (4, 256): [(2, 1)],
-    (2, 256): [(3, 1)],
-    (1, 256): [(4, 1)],
 }
 WINDOW_CTAS = ()   # the window kernel of round 1 is superseded by the element-owner kernel
 
@@ -149,6 +149,9 @@ def direct_instances():
                 for (minb, dflt) in variants:
                     if not dflt and amp != "c128":
                         continue
+                    out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
+            for (SU, NT), variants in DIRECT_EXTRA.get(amp, {}).items():
+                for (minb, dflt) in variants:
                     out.append((f"amajor_{amp}_d{dt}", amp, SU, NT, minb, dt, dflt))
     return out
 

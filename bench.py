@@ -57,12 +57,13 @@ def parse():
 
 
 def csrc_sha():
-    """Hash of the kernel sources: ncu captures under profiles/ are only quoted for the code they were taken from."""
+    """Hash of the forward-kernel sources (the .cuh files: kernels + their launch functions): ncu captures under profiles/
+    are only quoted for the kernels they were taken from."""
     import hashlib
     d = os.path.join(ROOT, "qkan_implementation_b200", "csrc")
     h = hashlib.sha256()
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
+        if f.endswith(".cuh"):
             h.update(f.encode())
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]

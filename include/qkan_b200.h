@@ -75,11 +75,13 @@ int qkan_layer_forward_peers(qkan_layer* layer, const double* x, int64_t B, void
 int qkan_layer_forward_multicast(qkan_layer* layer, const double* x, int64_t B, void* mc_out, int64_t row_offset,
                                  void* cuda_stream);
 
-/* Same call with HOST buffers.  Pinned (page-locked, device-mapped) buffers: zero-copy - the kernel itself streams
- * x from host memory (TMA bulk loads over PCIe) and stores every result straight into the host buffer, so there
- * are no staging copies and no chunk pipeline.  Pageable buffers (or QKAN_HOST_PATH=staged): the batch is cut in
- * chunks and H2D copy, kernel and D2H copy of consecutive chunks overlap on three streams.
- * Synchronous: returns when `out` (and `amps`) are complete. */
+/* Same call with HOST buffers (QKANLayer.forward with NumPy arrays, QKANLayer.py:77).  The batch is cut in chunks of about
+ * 8 MiB of traffic (at most 16, never less than one wave of the forward kernel) that overlap on three streams.  Pinned
+ * (page-locked, device-mapped) buffers, the default: the DMA engine copies x chunk by chunk while the kernel of the previous
+ * chunk stores its results straight into the host buffer (no result staging copy); the pipeline of a call is replayed as a
+ * CUDA graph while the caller keeps passing the same buffers.  QKAN_HOST_PATH = zero_copy (the kernel also reads x from host
+ * memory itself, one launch, no chunks) | staged (H2D copy, kernel, D2H copy; always for pageable buffers) | copy_out selects
+ * the other combinations.  Synchronous: returns when `out` (and `amps`) are complete. */
 int qkan_layer_forward_host(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps);
 
 /* Number of x entries seen outside [-1-1e-8, 1+1e-8] since the last call (the reference

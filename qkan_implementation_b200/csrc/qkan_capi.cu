@@ -591,6 +591,18 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
         }
         if (edge) cut[++nchunk] = B;
     }
+    if (const char* e = getenv("QKAN_HOST_CUTS")) {          // tuning aid: explicit chunk boundaries (samples, increasing)
+        nchunk = 0;
+        const char* q = e;
+        while (*q && nchunk < MAX_CHUNKS - 1) {
+            char* end = nullptr;
+            const long long v = strtoll(q, &end, 10);
+            if (end == q) break;
+            if (v > cut[nchunk] && v < B) cut[++nchunk] = v;
+            q = *end ? end + 1 : end;
+        }
+        cut[++nchunk] = B;
+    }
     const size_t asz = 2 * amp_real_size(l->dtype);
     auto enqueue = [&]() -> int {
         for (int i = 0; i < nchunk; ++i) {
@@ -622,7 +634,9 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
     };
     // CUDA graph of the pipeline: built on the second consecutive call with the same buffers, replayed afterwards.
     // Pinned buffers only (copies from pageable memory are staged by the driver and cannot be captured usefully).
-    const qkan_layer::HostKey key{x, out, amps, B, in_direct ? 1 : 0, out_direct ? 1 : 0, nchunk * 64 + (edge_div & 63)};
+    unsigned long long cut_hash = (unsigned long long)nchunk;
+    for (int i = 1; i <= nchunk; ++i) cut_hash = cut_hash * 1000003ull + (unsigned long long)cut[i];
+    const qkan_layer::HostKey key{x, out, amps, B, in_direct ? 1 : 0, out_direct ? 1 : 0, (int)(cut_hash & 0x7fffffffull)};
     auto same = [](const qkan_layer::HostKey& a, const qkan_layer::HostKey& b) {
         return a.x == b.x && a.out == b.out && a.amps == b.amps && a.B == b.B && a.in_direct == b.in_direct &&
                a.out_direct == b.out_direct && a.nchunk == b.nchunk;

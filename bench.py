@@ -528,7 +528,7 @@ def run_ours(a):
                             + ("This round's kernels run the CHEB sequence once per input element - the D+1 degree copies of a "
                                "block and the blocks that read the same input share it (circuit structure: CHEB does not act on deg, "
                                "the multiplexor's angle table has N distinct entries) - and SELECT once per (a,b,d) block, so they "
-                               "execute 8DN + 4NK(D+1) FP instructions per sample where round 1 executed NK(D+1)(8D+4); "
+                               "execute (12D-7)E + 4NK(D+1) FP instructions per sample for D <= 8 (CHEB in the sin-weighted basis: rotation entry (c, 1-c^2), no square root) and 8DE + 4NK(D+1) above, E = CHEB evaluations per sample, where round 1 executed NK(D+1)(8D+4); "
                                "*_per_block_basis credits the round-1 count for the same time (comparable with BENCH_r01), and is "
                                "> 1 when the saved arithmetic exceeds what the pipe could have done. "
                                if info.get("degree_factored") else "")

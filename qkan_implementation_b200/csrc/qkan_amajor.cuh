@@ -672,22 +672,31 @@ __global__ void __launch_bounds__(NT, MINB) qkan_block_elem_kernel(const BlockPa
     const long long chunk = (long long)SU * SPC;
     const long long n_chunks = (p.B + chunk - 1) / chunk;
     const size_t jstep = (size_t)D1 * G;                      // table entries between consecutive j of a lane
-    const int steps_per_row = p.passes * G;
     unsigned bad = 0;
 
+    // Loop order.  chunk-outer (p.window == 0): a chunk of samples walks all rows, i.e. the whole SELECT table, before the CTA
+    // moves on - fine while the table fits L1.  row-outer (p.window != 0, wide layers): all the CTA's chunks are taken through
+    // ONE row before the next row starts, so the row's slice of the table (passes K (D + 1) G entries; N784 K10 D5: 77 KB of
+    // the 752 KB) stays in L1 across the chunks of both resident CTAs instead of streaming from L2 once per chunk (the wait
+    // for those loads was 39 % of the warp samples at C4, profiles/r02F_ncu_c4.txt).  Every (sample, row) is still evaluated
+    // once, by the same code, and x is still read once: a row reads only its own window of the input row.
+    const bool row_outer = p.window != 0;
+    const int n_ob = row_outer ? p.brows : 1, rows_per = row_outer ? 1 : p.brows;
+    for (int ob = 0; ob < n_ob; ++ob)
     for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const long long s0 = c * chunk + slot;                // the lane's samples: s0 + j SPC
         const long long left = p.B - s0;                      // <= 0: the whole lane is beyond the batch (still runs: the butterfly needs every lane)
         const double* __restrict__ xs = p.x + (left > 0 ? s0 : 0) * p.N;
         const int xstride = SPC * p.N;
-        const int* xp = xe + g;
-        const CS<R>* wp = we + g;
+        const int bi0 = ob * rows_per;
+        const int* xp = xe + g + (size_t)bi0 * p.passes * G;
+        const CS<R>* wp = we + g + (size_t)bi0 * p.passes * p.K * jstep;
         // the first element's inputs
         int en = *xp;
         double xn[SU];
         QK_UNROLL
         for (int j = 0; j < SU; ++j) xn[j] = ((long long)j * SPC < left) ? xs[j * xstride + (en < 0 ? 0 : (en & 0xFFFFF))] : 0.0;
-        for (int bi = 0; bi < p.brows; ++bi) {
+        for (int bi = bi0; bi < bi0 + rows_per; ++bi) {
             A acc[SU];
             QK_UNROLL
             for (int j = 0; j < SU; ++j) set_amp(acc[j], 0.0);
@@ -776,6 +785,14 @@ cudaError_t launch_elem_impl(const BlockParams& p0, int G, int sm_count, cudaStr
     p.G = G; p.G_r = 1 << p.g_r_log2; p.G_k = 1 << p.g_k_log2;
     p.SPC = SPC; p.tile = (int)chunk;
     p.row_bytes = 0; p.plane_bytes = 0;
+    // row-outer order when the SELECT table does not fit L1 but one row's slice does (see the kernel)
+    {
+        const size_t entry = sizeof(CS<R>);
+        const size_t row_slice = (size_t)p.passes * p.K * (DT + 1) * G * entry, table = row_slice * p.brows;
+        int ro = (table > 96 * 1024 && row_slice <= 128 * 1024 && n_chunks >= 2 * grid) ? 1 : 0;
+        if (const char* e = getenv("QKAN_ELEM_ROW_OUTER")) ro = atoi(e) != 0;          // A/B aid
+        p.window = ro;
+    }
     if (grid_out) *grid_out = (int)grid;
     if (smem_out) *smem_out = 0;
     kern<<<(unsigned)grid, NT, 0, stream>>>(p);

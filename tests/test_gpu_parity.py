@@ -452,6 +452,33 @@ def test_any_width_creates_and_runs(Q, D):
             assert_close(y, o.forward_closed_form(x, W, N, K, D))
 
 
+@pytest.mark.parametrize("dtype", ["complex128", "complex64", "real64"])
+@pytest.mark.parametrize("N,K,D,B", [(784, 10, 5, 40_037), (300, 7, 3, 50_001), (100, 10, 5, 200_003)])
+def test_element_owner_loop_orders_agree(Q, monkeypatch, N, K, D, B, dtype):
+    """The element-owner kernel walks wide layers row-outer (all chunks of a CTA through one output row before the next, so the
+    row's slice of the SELECT table stays in L1) and everything else chunk-outer: every (sample, row) is evaluated by the same
+    code either way, so the two orders must give the same bits - ragged batch, out-of-range inputs and their count included."""
+    rng = np.random.default_rng(N + D)
+    x = rng.uniform(-1, 1, (B, N))
+    x[3, ::5] = 1.0
+    x[B - 2, 1::7] = -1.25
+    x[B // 2, 0] = 3.0
+    W = rng.uniform(-1, 1, (D + 1, N * K))
+    n_bad = int(((x < -1 - 1e-8) | (x > 1 + 1e-8)).sum())
+    xd, Wd = torch.from_numpy(x).cuda(), torch.from_numpy(W).cuda()
+    outs = []
+    for order in ("0", "1"):
+        monkeypatch.setenv("QKAN_ELEM_ROW_OUTER", order)
+        layer = Q.QKANLayer(N, K, D, dtype=dtype)
+        y = layer.forward(xd, Wd)
+        assert layer.kernel_info()["element_owner"] == 1
+        assert layer.out_of_range_count() == n_bad
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+    idx = np.concatenate([np.arange(8), np.arange(B - 8, B), [B // 2]])
+    assert_close(outs[1][torch.from_numpy(idx).cuda()].cpu().numpy(), o.forward_closed_form(x[idx], W, N, K, D), dtype)
+
+
 @pytest.mark.parametrize("N,K,D,B", [(4, 4, 3, 1_000_000),        # BASELINE configs[1]
                                      (16, 16, 8, 1_000_000),     # configs[2]
                                      (784, 10, 5, 100_000),      # configs[3]

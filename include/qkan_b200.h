@@ -84,6 +84,12 @@ int qkan_layer_forward_multicast(qkan_layer* layer, const double* x, int64_t B, 
  * the other combinations.  Synchronous: returns when `out` (and `amps`) are complete. */
 int qkan_layer_forward_host(qkan_layer* layer, const double* x, int64_t B, double* out, void* amps);
 
+/* The chunk schedule qkan_layer_forward_host uses for a batch of B samples of an N -> K layer whose forward kernel works in
+ * tiles of `tile_samples` samples and fills the GPU with `wave_samples` samples: cuts[0] = 0 < cuts[1] < ... < cuts[n] = B
+ * (cuts holds max_chunks + 1 entries), returns n >= 1 or a negative error code.  About 8 MiB of traffic per chunk, at most 16
+ * chunks, never less than one wave, boundaries on tile multiples.  Pure host arithmetic (no GPU needed). */
+int qkan_plan_host_chunks(int64_t B, int N, int K, int64_t tile_samples, int64_t wave_samples, int64_t* cuts, int max_chunks);
+
 /* Number of x entries seen outside [-1-1e-8, 1+1e-8] since the last call (the reference
  * prints them, ChebyshevStep.py:46-49).  Synchronises the device; resets the counter. */
 int qkan_layer_out_of_range(qkan_layer* layer, uint64_t* count);

@@ -20,7 +20,7 @@ PREPS = {"analytic": 1, "gates": 0}
 
 EXPORTS = [
     "qkan_layer_create", "qkan_layer_destroy", "qkan_layer_set_weights", "qkan_layer_forward",
-    "qkan_layer_forward_host", "qkan_layer_forward_peers", "qkan_layer_forward_multicast", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals", "qkan_layer_stage_snapshots",
+    "qkan_layer_forward_host", "qkan_plan_host_chunks", "qkan_layer_forward_peers", "qkan_layer_forward_multicast", "qkan_layer_out_of_range", "qkan_layer_info", "qkan_layer_diagonals", "qkan_layer_stage_snapshots",
     "qkan_forward", "qkan_measure_fma_peak", "qkan_last_error", "qkan_version", "qkan_simulate_circuit",
     "qkan_set_last_error",
     "qkan_measure_dmma_peak", "qkan_cheb_gram_workspace", "qkan_cheb_gram", "qkan_cheb_residuals_ctas", "qkan_cheb_residuals", "qkan_cheb_features",

@@ -508,6 +508,69 @@ extern "C" int qkan_layer_forward_multicast(qkan_layer* l, const double* x, int6
     return launch_on(l, x, B, nullptr, nullptr, (cudaStream_t)cuda_stream, nullptr, 0, row_offset, mc_out);
 }
 
+// Chunk schedule of qkan_layer_forward_host: cuts[0] = 0 < cuts[1] < ... < cuts[n] = B, returns n (<= max_chunks <= 64).
+// Enough chunks to overlap copy-in / compute / copy-out: about 8 MiB of traffic per chunk but at most 16 chunks (each DMA copy
+// carries ~10 us of fixed cost: N4 K4, 1M samples: 8 chunks 0.84 ms, 16 +9 %, 64 +60 %; N16 K16, 256 MB: 8 or 16 chunks 3.13 ms,
+// 32 chunks 3.26 ms), and never less than one full wave of the forward kernel (a chunk's kernel takes the time of one CTA chunk
+// however few CTAs it has: N784 K10 D5 cut into 64 chunks of 1 562 samples ran 17.2 ms against 11.8 ms with 8); every boundary a
+// multiple of the CTA tile `tile_samples`.  Making the first and the last chunk smaller (QKAN_HOST_EDGE_DIV > 1; nothing overlaps
+// the first copy-in and the last result write) or other boundaries (QKAN_HOST_CUTS) measured no better:
+// profiles/r02v_e2e_ab.txt, r02I_e2e_chunk_boundaries.txt.  Pure host arithmetic: exported so that it is tested without a GPU.
+extern "C" int qkan_plan_host_chunks(int64_t B, int N, int K, int64_t tile_samples, int64_t wave_samples, int64_t* cuts, int max_chunks) {
+    if (B < 1 || N < 1 || K < 1 || tile_samples < 1 || wave_samples < 1 || !cuts || max_chunks < 1)
+        return fail(QKAN_ERR_BAD_SHAPE, "qkan_plan_host_chunks: bad arguments");
+    if (max_chunks > MAX_CHUNKS) max_chunks = MAX_CHUNKS;
+    const int64_t spi = tile_samples, wave = wave_samples;
+    int64_t per = ((int64_t)8 << 20) / ((int64_t)(N + K) * 8);
+    if (per < 1) per = 1;
+    bool forced = false;
+    if (const char* e = getenv("QKAN_HOST_CHUNKS")) {        // tuning aid: this many uniform-size chunks
+        const int nc = atoi(e);
+        if (nc >= 1) { per = (B + nc - 1) / nc; forced = true; }
+    }
+    if (!forced) {
+        if (per * 16 < B) per = (B + 15) / 16;
+        if (per < wave) per = wave;
+    }
+    if (per * max_chunks < B) per = (B + max_chunks - 1) / max_chunks;
+    per = (per + spi - 1) / spi * spi;
+    int edge_div = 1;
+    if (const char* e = getenv("QKAN_HOST_EDGE_DIV")) edge_div = atoi(e);
+    int nchunk = 0;
+    cuts[0] = 0;
+    {
+        int64_t edge = edge_div > 1 ? (per / edge_div + spi - 1) / spi * spi : 0;
+        if (edge < spi || 2 * edge + per > B || max_chunks < 3) edge = 0;       // too small a batch for edges
+        const int64_t mid = B - 2 * edge;
+        const int room = max_chunks - (edge ? 2 : 0);
+        int nmid = forced ? (int)((mid + per - 1) / per)      // a forced count: rounded up
+                          : (int)(mid / per);                 // else rounded down: no chunk below `per` (one wave / ~8 MiB)
+        if (nmid < 1) nmid = 1;
+        if (nmid > room) nmid = room;
+        const int64_t mper = ((mid + nmid - 1) / nmid + spi - 1) / spi * spi;
+        if (edge) cuts[++nchunk] = edge;
+        for (int i = 0; i < nmid; ++i) {
+            int64_t hi = cuts[nchunk] + mper;
+            if (hi > B - edge || i == nmid - 1) hi = B - edge;
+            if (hi > cuts[nchunk]) cuts[++nchunk] = hi;
+        }
+        if (edge) cuts[++nchunk] = B;
+    }
+    if (const char* e = getenv("QKAN_HOST_CUTS")) {          // tuning aid: explicit chunk boundaries (samples, increasing)
+        nchunk = 0;
+        const char* q = e;
+        while (*q && nchunk < max_chunks - 1) {
+            char* end = nullptr;
+            const long long v = strtoll(q, &end, 10);
+            if (end == q) break;
+            if (v > cuts[nchunk] && v < B) cuts[++nchunk] = v;
+            q = *end ? end + 1 : end;
+        }
+        cuts[++nchunk] = B;
+    }
+    return nchunk;
+}
+
 extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B, double* out, void* amps) {
     NvtxRange nvtx_range("qkan_layer_forward_host");
     if (!l) return fail(QKAN_ERR_BAD_SHAPE, "null layer");
@@ -552,57 +615,12 @@ extern "C" int qkan_layer_forward_host(qkan_layer* l, const double* x, int64_t B
         CU(cudaStreamSynchronize(l->s_k));
         return QKAN_OK;
     }
-    // chunks: enough to overlap copy-in / compute / copy-out.  About 8 MiB of traffic per chunk but at most 16 chunks (each
-    // DMA copy carries ~10 us of fixed cost: N4 K4, 1M samples: 8 chunks 0.84 ms, 16 +9 %, 64 +60 %; N16 K16, 256 MB: 8 or 16
-    // chunks 3.13 ms, 32 chunks 3.26 ms), and never less than one full wave of the forward kernel (a chunk's kernel takes
-    // the time of one CTA chunk however few CTAs it has: N784 K10 D5 cut into 64 chunks of 1 562 samples ran 17.2 ms against
-    // 11.8 ms with 8), a multiple of the CTA tile.  Making the first and the last chunk smaller (QKAN_HOST_EDGE_DIV > 1;
-    // nothing overlaps the first copy-in and the last result write) measured no better: profiles/r02v_e2e_ab.txt.
+    // the chunk schedule (qkan_plan_host_chunks below: about 8 MiB of traffic per chunk, at most 16, never less than one wave)
     const int64_t spi = l->engine == 0 ? (l->bkern->NT >> (l->lay.g_r_log2 + l->lay.g_k_log2)) : l->kern->spi;
     const int64_t wave = l->engine == 0 ? (int64_t)l->sm_count * 2 * spi * (l->bkern->SU > 0 ? l->bkern->SU : 1) : spi;
-    int64_t per = ((int64_t)8 << 20) / ((int64_t)(l->N + l->K) * 8);
-    if (const char* e = getenv("QKAN_HOST_CHUNKS")) {        // tuning aid: this many uniform-size chunks
-        const int nc = atoi(e);
-        if (nc >= 1) per = (B + nc - 1) / nc;
-    } else {
-        if (per * 16 < B) per = (B + 15) / 16;
-        if (per < wave) per = wave;
-    }
-    if (per * MAX_CHUNKS < B) per = (B + MAX_CHUNKS - 1) / MAX_CHUNKS;
-    per = (per + spi - 1) / spi * spi;
-    int edge_div = 1;
-    if (const char* e = getenv("QKAN_HOST_EDGE_DIV")) edge_div = atoi(e);
-    int64_t cut[MAX_CHUNKS + 3];
-    int nchunk = 0;
-    cut[0] = 0;
-    {
-        int64_t edge = edge_div > 1 ? (per / edge_div + spi - 1) / spi * spi : 0;
-        if (edge < spi || 2 * edge + per > B) edge = 0;       // too small a batch for edges
-        int64_t mid = B - 2 * edge;
-        int nmid = (int)((mid + per - 1) / per);
-        if (nmid < 1) nmid = 1;
-        if (nmid > MAX_CHUNKS - 2) nmid = MAX_CHUNKS - 2;
-        int64_t mper = ((mid + nmid - 1) / nmid + spi - 1) / spi * spi;
-        if (edge) cut[++nchunk] = edge;
-        for (int i = 0; i < nmid; ++i) {
-            int64_t hi = cut[nchunk] + mper;
-            if (hi > B - edge || i == nmid - 1) hi = B - edge;
-            if (hi > cut[nchunk]) cut[++nchunk] = hi;
-        }
-        if (edge) cut[++nchunk] = B;
-    }
-    if (const char* e = getenv("QKAN_HOST_CUTS")) {          // tuning aid: explicit chunk boundaries (samples, increasing)
-        nchunk = 0;
-        const char* q = e;
-        while (*q && nchunk < MAX_CHUNKS - 1) {
-            char* end = nullptr;
-            const long long v = strtoll(q, &end, 10);
-            if (end == q) break;
-            if (v > cut[nchunk] && v < B) cut[++nchunk] = v;
-            q = *end ? end + 1 : end;
-        }
-        cut[++nchunk] = B;
-    }
+    int64_t cut[MAX_CHUNKS + 1];
+    const int nchunk = qkan_plan_host_chunks(B, l->N, l->K, spi, wave, cut, MAX_CHUNKS);
+    if (nchunk < 1) return nchunk < 0 ? nchunk : fail(QKAN_ERR_BAD_SHAPE, "internal: empty chunk schedule");
     const size_t asz = 2 * amp_real_size(l->dtype);
     auto enqueue = [&]() -> int {
         for (int i = 0; i < nchunk; ++i) {

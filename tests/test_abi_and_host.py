@@ -60,6 +60,64 @@ def test_degree_abi_argument_errors_without_gpu():
             DegreeOptimizer([3, 1], 2).evaluate_degree(np.zeros((5, 3)), np.zeros(5))
 
 
+def _plan_chunks(lib, B, N, K, tile, wave, max_chunks=64):
+    cuts = (ctypes.c_int64 * (max_chunks + 1))()
+    lib.qkan_plan_host_chunks.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.c_int]
+    n = lib.qkan_plan_host_chunks(B, N, K, tile, wave, cuts, max_chunks)
+    return n, list(cuts[:max(n, 0) + 1])
+
+
+def test_host_chunk_schedule(monkeypatch):
+    """Host logic of qkan_layer_forward_host (pure arithmetic, no GPU): the chunk boundaries cover the batch, sit on tile
+    multiples, keep about 8 MiB of traffic per chunk with at most 16 chunks, and never cut below one kernel wave."""
+    from qkan_implementation_b200 import _binding as b
+    lib = b.lib()
+    for var in ("QKAN_HOST_CHUNKS", "QKAN_HOST_EDGE_DIV", "QKAN_HOST_CUTS"):
+        monkeypatch.delenv(var, raising=False)
+    rng = np.random.default_rng(0)
+    shapes = [(4, 4, 64, 75_776), (16, 16, 16, 18_944), (784, 10, 16, 18_944), (8, 8, 32, 37_888), (3, 5, 1, 1)]
+    batches = [1, 5, 63, 64, 65, 4096, 100_000, 1_000_000, 10_000_019] + [int(v) for v in rng.integers(1, 3_000_000, 20)]
+    for (N, K, tile, wave) in shapes:
+        for B in batches:
+            n, cuts = _plan_chunks(lib, B, N, K, tile, wave)
+            assert 1 <= n <= 16, (N, K, B, n)
+            assert cuts[0] == 0 and cuts[-1] == B and all(a < c for a, c in zip(cuts, cuts[1:]))
+            assert all(c % tile == 0 for c in cuts[1:-1])
+            sizes = np.diff(cuts)
+            per = max((8 << 20) // ((N + K) * 8), -(-B // 16), wave)       # ~8 MiB of traffic, at most 16 chunks, one wave
+            if n > 1:                                          # more than one chunk only when every chunk is at least `per` ...
+                assert sizes[:-1].min() >= per and sizes[-1] >= per - n * tile
+                assert sizes.max() == sizes[0] and len(set(sizes[:-1])) == 1     # ... and the chunks are even (the last takes the remainder)
+                assert sizes[0] < 2 * per + tile
+            else:
+                assert B < 2 * (per + tile)
+    # the BASELINE shapes: 1 M samples of N4 K4 -> 7 chunks of ~9 MB; 100 k samples of N784 K10 -> whole waves, not 64 slivers
+    n, cuts = _plan_chunks(lib, 1_000_000, 4, 4, 64, 75_776)
+    assert n == 7 and cuts[1] == 142_912
+    n, cuts = _plan_chunks(lib, 100_000, 784, 10, 16, 18_944)
+    assert n <= 6 and min(np.diff(cuts)[:-1]) >= 18_944
+    # tuning aids: a fixed number of uniform chunks, smaller edge chunks, explicit boundaries
+    monkeypatch.setenv("QKAN_HOST_CHUNKS", "4")
+    n, cuts = _plan_chunks(lib, 1_000_000, 4, 4, 64, 75_776)
+    assert n == 4 and cuts[-1] == 1_000_000
+    monkeypatch.setenv("QKAN_HOST_CHUNKS", "1000")
+    n, cuts = _plan_chunks(lib, 1_000_000, 4, 4, 64, 75_776)
+    assert n <= 64 and cuts[-1] == 1_000_000 and all(a < c for a, c in zip(cuts, cuts[1:]))
+    monkeypatch.delenv("QKAN_HOST_CHUNKS")
+    monkeypatch.setenv("QKAN_HOST_EDGE_DIV", "4")
+    n, cuts = _plan_chunks(lib, 1_000_000, 4, 4, 64, 75_776)
+    sizes = np.diff(cuts)
+    assert sizes[0] == sizes[-1] and sizes[0] * 3 < sizes[1] and cuts[-1] == 1_000_000
+    monkeypatch.delenv("QKAN_HOST_EDGE_DIV")
+    monkeypatch.setenv("QKAN_HOST_CUTS", "1000,500,70000,2000000")
+    n, cuts = _plan_chunks(lib, 100_000, 4, 4, 64, 75_776)
+    assert cuts == [0, 1000, 70000, 100_000]
+    monkeypatch.delenv("QKAN_HOST_CUTS")
+    assert _plan_chunks(lib, 0, 4, 4, 64, 64)[0] == b.ERR_BAD_SHAPE
+    assert lib.qkan_plan_host_chunks(10, 4, 4, 64, 64, None, 8) == b.ERR_BAD_SHAPE
+
+
 def test_no_cpu_fallback_when_no_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

@@ -104,6 +104,45 @@ __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, lon
     }
 }
 
+// Straight-line form of fill_chunk: every slot of the thread is evaluated with predicated stores and no branch (the branchy
+// form above spent a fifth of the kernel's warp samples on BRA / BSSY / BSYNC, profiles/r02x_ncu_gram.txt).  The columns
+// beyond P are zeroed once per launch instead of once per chunk (nothing else ever writes them).
+#ifndef GRAM_FLAT_FILL
+#define GRAM_FLAT_FILL 1
+#endif
+template <int MAXI, int D1T>
+__device__ __forceinline__ void fill_chunk_flat(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI],
+                                                int f_lo, int nf) {
+    const int D1 = D1T > 0 ? D1T : p.D + 1;
+    const int kk = threadIdx.x & (KC - 1), jrow = threadIdx.x >> 5;
+    const double lv = s0 + kk < p.n ? 1.0 : 0.0;         // rows beyond the slice are zero rows (last chunk only)
+#pragma unroll
+    for (int it = 0; it < MAXI; ++it) {
+        const int j = jrow + it * (GRAM_THREADS / KC);
+        const bool isy = j == nf, feat = j < nf;         // slot nf is the y column; slots beyond it do nothing
+        const double v = xv[it];
+        const int cbase = isy ? p.P - c0 : (f_lo + j) * D1 - c0;
+        double* q = dst + cbase * LDK + kk;
+        const double xc = clip_unit(v);
+        if ((feat || isy) && (unsigned)cbase < (unsigned)TILE) q[0] = isy ? lv * v : lv;
+        double t0 = lv, t1 = lv * xc;
+        if constexpr (D1T > 0) {
+#pragma unroll
+            for (int k = 1; k < D1T; ++k) {
+                if (feat && (unsigned)(cbase + k) < (unsigned)TILE) q[k * LDK] = t1;
+                const double t2 = 2.0 * xc * t1 - t0;
+                t0 = t1; t1 = t2;
+            }
+        } else {
+            for (int k = 1; k < D1; ++k) {
+                if (feat && (unsigned)(cbase + k) < (unsigned)TILE) q[k * LDK] = t1;
+                const double t2 = 2.0 * xc * t1 - t0;
+                t0 = t1; t1 = t2;
+            }
+        }
+    }
+}
+
 // Rejected variants (correct, A/B on one box, profiles/README.md): double-buffered chunks with one barrier (round 1),
 // a producer warp + mbarrier ring, cp.async input staging (round 2, first session), and chunks double buffered with the
 // production of chunk i + 1 sliced between the eight DMMA groups of chunk i (3 CTAs per SM: 3.55 ms against 3.49 ms);
@@ -172,10 +211,20 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
         prefetch(s_begin, xa, fa_lo, nfa);
         if (!diag) prefetch(s_begin, xb, fb_lo, nfb);
     }
+    // compile-time degree (D <= 4): the straight-line producer (774 456 x 79: D = 3 3.50 -> 3.39 ms, D = 1 1.59 -> 1.53 ms); run-time
+    // degree: the branchy one (a run-time loop of predicated stores is slower: D = 8, 200 k rows: 4.86 against 5.70 ms)
+    constexpr bool flat = GRAM_FLAT_FILL && D1T > 0;
+    if constexpr (flat)
+        for (int i = threadIdx.x; i < TILE * LDK; i += GRAM_THREADS) As[i] = Bs[i] = 0.0;    // the columns beyond P stay zero
     for (long long s0 = s_begin; s0 < s_end; s0 += KC) {
         __syncthreads();                                 // the previous chunk's fragments are consumed
-        fill_chunk<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
-        if (!diag) fill_chunk<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
+        if constexpr (flat) {
+            fill_chunk_flat<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
+            if (!diag) fill_chunk_flat<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
+        } else {
+            fill_chunk<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
+            if (!diag) fill_chunk<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
+        }
         __syncthreads();
         if (s0 + KC < s_end) {                           // next chunk's x / y: in flight during the MMAs
             prefetch(s0 + KC, xa, fa_lo, nfa);

@@ -104,8 +104,7 @@ AMAJOR = {
 # measured best on every BASELINE shape: four samples per lane, 256-thread CTAs, two CTAs per SM
 # (profiles/r02e_tune_direct.jsonl, r02d_tune_direct_all.jsonl)
 DIRECT = {
-    (4, 256): [(2, 1)],
-    (3, 128): [(5, 0), (4, 0)],   # experiment      # (2, 256) x 3 CTAs, (4, 128) x 4 and (2, 128) x 6 measured equal or slower, with run-time and with
+    (4, 256): [(2, 1)],      # (2, 256) x 3 CTAs, (4, 128) x 4 and (2, 128) x 6 measured equal or slower, with run-time and with
                              # compile-time lanes per sample (profiles/r02e_tune_direct.jsonl, r02u_tune_direct.jsonl), and so did three samples per lane
                              # at 94 registers with 4 or 5 CTAs of 128 threads (20 resident warps: occupancy is not the limiter): not built
 }

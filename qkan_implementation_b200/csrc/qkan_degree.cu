@@ -443,6 +443,336 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
         for (int i = threadIdx.x; i < D1 * P; i += RES_THREADS) xtr[(size_t)blockIdx.x * D1 * P + i] = s_xtr[i];
 }
 
+// ---- residual pass, tile form (D <= 4, F <= 128: the reference's workload, 79 features at max_degree 3)
+// The warp-per-sample kernel above spends 390 of its 540 instructions per sample on coefficient addresses / loads and on
+// the 5-step butterflies of the D + 1 predictions (profiles/r02Z_ncu_degree_kernels.txt: 228 registers, one CTA per SM,
+// FP64 pipe 22 % busy, 0.66 ms at 774 456 x 79 where the x rows alone stream from HBM in 0.07 ms).  Here a CTA walks
+// tiles of 64 samples, staged by 1-D TMA bulk copies (two tiles in flight), in two phases with different lane mappings:
+//   phase 1 (predictions): four lanes per sample, each over a contiguous quarter of the features; the coefficients of a
+//       feature are one 16-byte-aligned run in shared memory (immediate offsets, no index arithmetic), the T_0 columns
+//       are summed once per launch (they do not depend on x), and the four partial predictions meet in two xor steps;
+//   phase 2 (X^T r, only when requested): a warp per sample, a lane per feature as above, with the residuals of the
+//       sample broadcast from shared memory; the accumulators stay in registers for the whole launch.
+// Same outputs (per-CTA partial sums in the same layout) as the warp-per-sample kernel.
+constexpr int RT_THREADS = 256;
+constexpr int RT_TS1 = 64;                                  // samples per tile and per phase-1 round (8 warps x 8 samples); tiles hold
+                                                            // SPL rounds, SPL = 2 when two tiles of 128 samples fit shared memory
+
+__host__ __device__ constexpr int rt_tri(int D1) { return D1 * (D1 - 1) / 2; }           // (k, d) pairs with 1 <= k <= d < D1
+__host__ __device__ constexpr int rt_cw(int D1) { return (rt_tri(D1) + 1) & ~1; }        // doubles per feature (even: LDS.128)
+__host__ __device__ constexpr int rt_idx(int D1, int k, int d) {                         // position of (k, d) in a feature's run
+    int i = 0;
+    for (int kk = 1; kk < k; ++kk) i += D1 - kk;
+    return i + (d - k);
+}
+// The coefficient runs of the four feature quarters start 8 banks apart (quarter stride = 4 mod 16 doubles): the 16-byte loads of
+// a quarter warp - two samples x four quarters - then touch four different bank groups (at F = 79, D = 3 the unpadded stride put
+// quarters 0 / 2 and 1 / 3 on the same banks: every coefficient load took two passes).
+__host__ __device__ inline int rt_qstride(int F, int D1) {
+    const int raw = ((F + 3) >> 2) * rt_cw(D1);
+    return raw == 0 ? 0 : raw + ((4 - raw % 16) + 16) % 16;
+}
+// shared memory in doubles: xs[2][TS F] | cf[4 quarter strides] | c0[D1P] | rs[TS D1P] | s_xtr[D1 P] | s_red[warps][3 D1 + 4] | mbar[2]
+struct ResTileSmem {
+    int tile, cf, c0, rs, xtr, red, mbar, total;
+};
+__host__ __device__ inline ResTileSmem rt_smem(int F, int D1, bool want_xtr, int TS) {
+    ResTileSmem s;
+    const int D1P = (D1 + 1) & ~1;
+    s.tile = TS * F;
+    s.cf = 2 * s.tile;
+    s.c0 = s.cf + 4 * rt_qstride(F, D1);
+    s.rs = s.c0 + D1P;
+    s.xtr = s.rs + TS * D1P;
+    s.red = s.xtr + (want_xtr ? ((D1 * D1 * F + 1) & ~1) : 0);
+    s.mbar = s.red + (((RT_THREADS / 32) * (3 * D1 + 4) + 1) & ~1);
+    s.total = s.mbar + 2;
+    return s;
+}
+
+__device__ __forceinline__ unsigned rt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rt_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void rt_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(rt_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rt_mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = rt_smem_u32(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void rt_tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(rt_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(rt_smem_u32(bar))
+                 : "memory");
+}
+
+template <int D1, int JF, int SPL>
+__global__ void __launch_bounds__(RT_THREADS, 1) qkan_cheb_residual_tile_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                                               const double* __restrict__ w, long long n, int F,
+                                                                               const double* __restrict__ coef, double ybar, double* sums,
+                                                                               double* tail, double* xtr, int tma_ok) {
+    extern __shared__ __align__(128) double rt_sm[];
+    constexpr int TS = RT_TS1 * SPL, NT = RT_THREADS, NW = NT / 32;
+    constexpr int CW = rt_cw(D1), CWA = CW > 0 ? CW : 2, D1P = (D1 + 1) & ~1;
+    const int P = F * D1;
+    const ResTileSmem L = rt_smem(F, D1, xtr != nullptr, TS);
+    const int FQ = (F + 3) >> 2, QS = rt_qstride(F, D1);     // features per quarter, its stride in cf
+    double* const xs = rt_sm;
+    double* const cf = rt_sm + L.cf;
+    double* const c0 = rt_sm + L.c0;
+    double* const rs = rt_sm + L.rs;
+    double* const s_xtr = rt_sm + L.xtr;
+    double* const s_red = rt_sm + L.red;
+    unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(rt_sm + L.mbar);
+    const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+
+    if (tid == 0) {
+        rt_mbar_init(&mbar[0], 1);
+        rt_mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // a feature's coefficients of degree k >= 1 as one run: cf[(f / FQ) QS + (f % FQ) CW + rt_idx(k, d)] = coef[d][k F + f], d >= k
+    if constexpr (CW > 0) {
+        for (int i = tid; i < F * CW; i += NT) {
+            const int f = i / CW;
+            int rem = i - f * CW, k = 1;
+            while (k < D1 && rem >= D1 - k) { rem -= D1 - k; ++k; }
+            const int fq = f / FQ;
+            cf[fq * QS + (f - fq * FQ) * CW + (i - f * CW)] = k < D1 ? coef[(size_t)(k + rem) * P + (size_t)k * F + f] : 0.0;
+        }
+    }
+    // the T_0 columns do not depend on x: their coefficients are summed once (warp d sums fit d)
+    for (int d = wq; d < D1P; d += NW) {
+        double s = 0.0;
+        if (d < D1)
+            for (int f = lane; f < F; f += 32) s += coef[(size_t)d * P + f];
+        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0) c0[d] = s;
+    }
+    if (xtr)
+        for (int i = tid; i < D1 * P; i += NT) s_xtr[i] = 0.0;
+
+    const long long n_tiles = (n + TS - 1) / TS;
+    auto tile_n = [&](long long t) -> int {
+        const long long left = n - t * TS;
+        return left < TS ? (int)left : TS;
+    };
+    auto by_tma = [&](long long t) -> bool { return tma_ok && ((tile_n(t) * F) & 1) == 0; };
+    auto issue = [&](long long t, int b) {
+        const int cnt = tile_n(t) * F;
+        const double* src = x + (size_t)t * L.tile;
+        double* dst = xs + (size_t)b * L.tile;
+        if (by_tma(t)) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                rt_mbar_expect_tx(&mbar[b], (unsigned)cnt * 8u);
+                rt_tma_load_1d(dst, src, (unsigned)cnt * 8u, &mbar[b]);
+            }
+        } else {
+            for (int q = tid; q < cnt; q += NT) dst[q] = src[q];
+        }
+    };
+    __syncthreads();                                         // barriers initialised, tables complete
+
+    double a_sse[D1], a_wsse[D1], a_r[D1];
+#pragma unroll
+    for (int d = 0; d < D1; ++d) a_sse[d] = a_wsse[d] = a_r[d] = 0.0;
+    double a_tot = 0.0, a_wyy = 0.0, a_w = 0.0, a_y = 0.0;
+    // X^T r accumulators of the lane's features for the degrees k >= 1 (the T_0 rows are sum r_d for every feature: a_r)
+    constexpr int KX = D1 > 1 ? D1 - 1 : 1;
+    double a_x[JF][KX][D1];                                  // [feature slot][degree k - 1][fit d]
+#pragma unroll
+    for (int jj = 0; jj < JF; ++jj)
+#pragma unroll
+        for (int k = 0; k < KX; ++k)
+#pragma unroll
+            for (int d = 0; d < D1; ++d) a_x[jj][k][d] = 0.0;
+
+    const long long step = gridDim.x;
+    long long t = blockIdx.x;
+    if (t < n_tiles) issue(t, 0);
+    if (t + step < n_tiles) issue(t + step, 1);
+    __syncthreads();                                         // (tiles staged by plain loads)
+    unsigned ph0 = 0, ph1 = 0;
+    int b = 0;
+    const int sl = lane >> 2, q4 = lane & 3;
+    const int st = wq * 8 + sl;                              // phase 1: the lane's sample of each round of 64
+    const int f_lo = q4 * FQ < F ? q4 * FQ : F, f_hi = f_lo + FQ < F ? f_lo + FQ : F;
+    const double* const cfq = cf + q4 * QS - f_lo * CW;      // + f CW = the run of feature f of this lane's quarter
+    const bool want_x = xtr != nullptr && D1 > 1;
+    for (; t < n_tiles; t += step, b ^= 1) {
+        const int nsamp = tile_n(t);
+        if (by_tma(t)) {
+            if (b == 0) { rt_mbar_wait(&mbar[0], ph0); ph0 ^= 1; }
+            else        { rt_mbar_wait(&mbar[1], ph1); ph1 ^= 1; }
+        }
+        double* const xt = xs + (size_t)b * L.tile;
+        if constexpr (D1 > 1) {
+            // ---- clip pass (np.clip, ChebyshevStep.py:52): only inputs with |v| >= 1 (or NaN) can change, decided on the high
+            // words with integer instructions, two inputs per step; the phases below then read clipped inputs
+            const int cnt = nsamp * F;
+            double2* const x2p = reinterpret_cast<double2*>(xt);
+            for (int i = tid; i < (cnt >> 1); i += NT) {
+                const double2 v = x2p[i];
+                const unsigned h0 = (unsigned)__double2hiint(v.x) & 0x7fffffffu, h1 = (unsigned)__double2hiint(v.y) & 0x7fffffffu;
+                if ((h0 > h1 ? h0 : h1) >= 0x3ff00000u) x2p[i] = make_double2(clip_unit(v.x), clip_unit(v.y));
+            }
+            if ((cnt & 1) && tid == 0) xt[cnt - 1] = clip_unit(xt[cnt - 1]);
+            __syncthreads();
+        }
+        {   // ---- phase 1: predictions of the D + 1 fits for the lane's SPL samples, residuals, the sums of the scores
+            bool valid[SPL];
+            double yv[SPL], wv[SPL], pred[SPL][D1];
+#pragma unroll
+            for (int sp = 0; sp < SPL; ++sp) {
+                valid[sp] = st + sp * RT_TS1 < nsamp;
+                const long long s = t * TS + st + sp * RT_TS1;
+                yv[sp] = 0.0; wv[sp] = 1.0;
+                if (valid[sp]) {
+                    yv[sp] = y[s];
+                    if (w) wv[sp] = w[s];
+                }
+#pragma unroll
+                for (int d = 0; d < D1; ++d) pred[sp][d] = q4 == 0 ? c0[d] : 0.0;
+            }
+            if constexpr (D1 > 1) {
+                const double* xr = xt + st * F;
+                for (int f = f_lo; f < f_hi; ++f) {
+                    double cw[CWA];
+                    const double2* cp = reinterpret_cast<const double2*>(cfq + f * CW);
+#pragma unroll
+                    for (int i = 0; i < CW / 2; ++i) {
+                        const double2 v = cp[i];
+                        cw[2 * i] = v.x;
+                        cw[2 * i + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int sp = 0; sp < SPL; ++sp) {
+                        const double xc = xr[sp * RT_TS1 * F + f];
+                        const double x2 = xc + xc;
+                        double t0 = 1.0, t1 = xc;
+#pragma unroll
+                        for (int k = 1; k < D1; ++k) {
+#pragma unroll
+                            for (int d = k; d < D1; ++d) pred[sp][d] = fma(t1, cw[rt_idx(D1, k, d)], pred[sp][d]);
+                            const double t2 = fma(x2, t1, -t0);
+                            t0 = t1; t1 = t2;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int sp = 0; sp < SPL; ++sp) {
+#pragma unroll
+                for (int d = 0; d < D1; ++d) {
+                    pred[sp][d] += __shfl_xor_sync(0xffffffffu, pred[sp][d], 1);
+                    pred[sp][d] += __shfl_xor_sync(0xffffffffu, pred[sp][d], 2);
+                }
+                if (valid[sp] && q4 == 0) {
+#pragma unroll
+                    for (int d = 0; d < D1; ++d) {
+                        const double r = yv[sp] - pred[sp][d];
+                        a_sse[d] = fma(r, r, a_sse[d]);
+                        a_wsse[d] = fma(wv[sp] * r, r, a_wsse[d]);
+                        a_r[d] += r;
+                        if (want_x) rs[(st + sp * RT_TS1) * D1P + d] = r;
+                    }
+                    a_tot = fma(yv[sp] - ybar, yv[sp] - ybar, a_tot);
+                    a_wyy = fma(wv[sp] * yv[sp], yv[sp], a_wyy);
+                    a_w += wv[sp];
+                    a_y += yv[sp];
+                }
+            }
+        }
+        __syncthreads();                                     // residuals of the tile in rs; phase 1 done with xt
+        if constexpr (D1 > 1) {
+            if (want_x) {   // ---- phase 2: X^T r of the tile for the degrees k >= 1 (warp per sample, lane per feature)
+                for (int s2 = wq; s2 < nsamp; s2 += NW) {
+                    const double* xr = xt + s2 * F;
+                    double r[D1P];
+                    const double2* rp = reinterpret_cast<const double2*>(rs + s2 * D1P);
+#pragma unroll
+                    for (int i = 0; i < D1P / 2; ++i) {
+                        const double2 v = rp[i];
+                        r[2 * i] = v.x;
+                        r[2 * i + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < JF; ++jj) {
+                        // a lane past the row (f >= F) reads the next row / the tables: its sums are never flushed
+                        const double xc = xr[lane + 32 * jj];
+                        const double x2 = xc + xc;
+                        double t0 = 1.0, t1 = xc;
+#pragma unroll
+                        for (int k = 1; k < D1; ++k) {
+#pragma unroll
+                            for (int d = 0; d < D1; ++d) a_x[jj][k - 1][d] = fma(t1, r[d], a_x[jj][k - 1][d]);
+                            const double t2 = fma(x2, t1, -t0);
+                            t0 = t1; t1 = t2;
+                        }
+                    }
+                }
+                __syncthreads();                             // rs and xt free again
+            }
+        }
+        if (t + 2 * step < n_tiles) issue(t + 2 * step, b);  // lands while the next tile is evaluated
+    }
+
+    if constexpr (D1 > 1) {
+        if (want_x) {                                        // one flush per warp
+#pragma unroll
+            for (int jj = 0; jj < JF; ++jj) {
+                const int f = lane + 32 * jj;
+                if (f < F) {
+#pragma unroll
+                    for (int k = 1; k < D1; ++k)
+#pragma unroll
+                        for (int d = 0; d < D1; ++d) atomicAdd(&s_xtr[(size_t)d * P + k * F + f], a_x[jj][k - 1][d]);
+                }
+            }
+        }
+    }
+    constexpr int Q = 2 * D1 + 4, QR = Q + D1;               // the outputs' sums, then sum r_d
+    {
+        double v[QR];
+#pragma unroll
+        for (int d = 0; d < D1; ++d) { v[2 * d] = a_sse[d]; v[2 * d + 1] = a_wsse[d]; v[Q + d] = a_r[d]; }
+        v[2 * D1] = a_tot; v[2 * D1 + 1] = a_wyy; v[2 * D1 + 2] = a_w; v[2 * D1 + 3] = a_y;
+#pragma unroll
+        for (int i = 0; i < QR; ++i) {
+            for (int m = 16; m >= 1; m >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], m);
+            if (lane == 0) s_red[wq * QR + i] = v[i];
+        }
+    }
+    __syncthreads();
+    if (tid < QR) {
+        double sacc = 0.0;
+        for (int wi = 0; wi < NW; ++wi) sacc += s_red[wi * QR + tid];
+        if (tid < 2 * D1) sums[(size_t)blockIdx.x * 2 * D1 + tid] = sacc;
+        else if (tid < Q) tail[(size_t)blockIdx.x * 4 + tid - 2 * D1] = sacc;
+        else if (xtr) {                                      // the T_0 rows of X^T r_d: sum r_d for every feature
+            const int d = tid - Q;
+            for (int f = 0; f < F; ++f) s_xtr[(size_t)d * P + f] = sacc;
+        }
+    }
+    __syncthreads();
+    if (xtr)
+        for (int i = tid; i < D1 * P; i += NT) xtr[(size_t)blockIdx.x * D1 * P + i] = s_xtr[i];
+}
+
 __global__ void qkan_cheb_features_kernel(const double* x, long long n, int F, int D, double* out) {
     // out [D+1][n][F]: the reference's transforms[d] (DegreeOptimizer.py:96-119)
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,9 +867,49 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
     int ctas = 0;
     qkan_cheb_residuals_ctas(&ctas);
     const int D1 = D + 1, P = F * D1;
+    cudaError_t e = cudaSuccess;
+    // tile kernel: D <= 4, F <= 128, the lane's X^T r accumulators within 64 doubles, tiles + tables within 200 KiB
+    {
+        const int jf = (F + 31) / 32;
+        // two rounds of 64 samples per tile (each coefficient load serves two samples per lane) when that fits shared memory
+        const size_t tsmem2 = (size_t)rt_smem(F, D1, xtr != nullptr, 2 * RT_TS1).total * sizeof(double);
+        const int spl = tsmem2 <= 200 * 1024 ? 2 : 1;
+        const size_t tsmem = spl == 2 ? tsmem2 : (size_t)rt_smem(F, D1, xtr != nullptr, RT_TS1).total * sizeof(double);
+        const char* force = getenv("QKAN_RES_KERNEL");           // A/B aid: "warp" = the warp-per-sample kernel
+        const bool warp_only = force && force[0] == 'w';
+        if (!warp_only && D1 <= 5 && jf <= 4 && jf * D1 * D1 <= 64 && tsmem <= 200 * 1024) {
+            const int tma_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+#define QK_RT_LAUNCH1(D1V, JFV, SPLV)                                                                                               \
+    {                                                                                                                                \
+        e = cudaFuncSetAttribute(qkan_cheb_residual_tile_kernel<D1V, JFV, SPLV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                 (int)tsmem);                                                                                        \
+        if (e == cudaSuccess)                                                                                                        \
+            qkan_cheb_residual_tile_kernel<D1V, JFV, SPLV><<<ctas, RT_THREADS, tsmem, (cudaStream_t)cuda_stream>>>(                  \
+                x, y, w, n, F, coef, ybar, sums, tail, xtr, tma_ok);                                                                 \
+    }
+#define QK_RT_LAUNCH(D1V, JFV)                                                                                                       \
+    {                                                                                                                                \
+        if (spl == 2) QK_RT_LAUNCH1(D1V, JFV, 2) else QK_RT_LAUNCH1(D1V, JFV, 1)                                                     \
+    }
+#define QK_RT_CASE(D1V)                                                                                                              \
+    case D1V:                                                                                                                        \
+        if (jf == 1) QK_RT_LAUNCH(D1V, 1)                                                                                            \
+        else if (jf == 2) QK_RT_LAUNCH(D1V, 2)                                                                                       \
+        else if (jf == 3) QK_RT_LAUNCH(D1V, (3 * D1V * D1V <= 64 ? 3 : 1))                                                           \
+        else QK_RT_LAUNCH(D1V, (4 * D1V * D1V <= 64 ? 4 : 1))                                                                        \
+        break;
+            switch (D1) { QK_RT_CASE(1) QK_RT_CASE(2) QK_RT_CASE(3) QK_RT_CASE(4) QK_RT_CASE(5) }
+#undef QK_RT_CASE
+#undef QK_RT_LAUNCH
+#undef QK_RT_LAUNCH1
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(qkan_cheb_residual_tile_kernel)");
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_residual_tile_kernel launch");
+            return QKAN_OK;
+        }
+    }
     const size_t smem = ((xtr ? (size_t)D1 * P : 0) + (size_t)(RES_THREADS / 32) * (2 * D1 + 4)) * sizeof(double);
     if (smem > 200 * 1024) return fail(QKAN_ERR_UNSUPPORTED, "qkan_cheb_residuals: (D+1)^2 F too large for the refinement accumulators");
-    cudaError_t e = cudaSuccess;
 #define QK_RES_LAUNCH(D1V, JFV)                                                                                                      \
     {                                                                                                                                \
         e = cudaFuncSetAttribute(qkan_cheb_residual_kernel<D1V, JFV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \

@@ -102,3 +102,57 @@ def test_large_fit_satisfies_normal_equations(Q):
         Pd = F * (d + 1)
         scale = np.sqrt(np.diag(eng.last["gram"])[:Pd] * float(t[0] + n * eng.last["ybar"] ** 2))
         assert np.abs(xr[d, :Pd] / scale).max() <= 1e-9
+
+
+RES_SHAPES = [(1, 1, 0), (7, 3, 1), (65, 5, 3), (1000, 79, 3), (4097, 16, 4), (5000, 21, 2), (777, 128, 2), (513, 33, 1),
+              (129, 64, 0), (64, 79, 3), (20_001, 79, 3),            # tile kernel (D <= 4, F <= 128)
+              (300, 2, 16), (400, 79, 5), (257, 130, 2)]            # warp-per-sample kernel
+
+
+@pytest.mark.parametrize("kernel", ["tile", "warp"])
+@pytest.mark.parametrize("n,F,D", RES_SHAPES)
+def test_residual_sums_match_numpy(Q, monkeypatch, kernel, n, F, D):
+    """qkan_cheb_residuals against NumPy on the same inputs: residual sums of all D + 1 fits, the totals behind R^2 and
+    X_D^T r_d (DegreeOptimizer.py:148-153, :277-312).  Both kernels (the tile kernel serves D <= 4, F <= 128; the
+    warp-per-sample kernel everything else, and every shape when QKAN_RES_KERNEL=warp), inputs beyond [-1, 1] (clipped),
+    ragged last tiles, weighted and unweighted, and an x that is not 16-byte aligned (no TMA: plain loads)."""
+    from qkan_implementation_b200.degree_optimizer import ChebyshevLeastSquares
+    if kernel == "warp":
+        monkeypatch.setenv("QKAN_RES_KERNEL", "warp")
+    else:
+        monkeypatch.delenv("QKAN_RES_KERNEL", raising=False)
+    rng = np.random.default_rng(1000 * n + 10 * F + D)
+    D1, P = D + 1, F * (D + 1)
+    xh = rng.normal(0.0, 0.7, (n, F))
+    yh = rng.normal(0.3, 1.0, n)
+    wh = rng.uniform(0.5, 1.5, n)
+    coef = np.zeros((D1, P))
+    for d in range(D1):
+        coef[d, :F * (d + 1)] = rng.normal(0.0, 0.3, F * (d + 1))
+    ybar = float(yh.mean())
+    xc = np.clip(xh, -1.0, 1.0)
+    T = [np.ones_like(xc), xc]
+    for k in range(2, D1):
+        T.append(2.0 * xc * T[-1] - T[-2])
+    X = np.hstack(T[:D1])                                    # degree-major columns k F + f, the reference's np.hstack order
+    R = yh[:, None] - X @ coef.T                             # [n, D+1]
+    eng = ChebyshevLeastSquares(D)
+    for aligned in (True, False):
+        if aligned:
+            xd = torch.from_numpy(xh).cuda()
+        else:
+            base = torch.empty(n * F + 1, dtype=torch.float64, device="cuda")
+            xd = base[1:].view(n, F)
+            xd.copy_(torch.from_numpy(xh))
+            assert xd.data_ptr() % 16 == 8
+        yd = torch.from_numpy(yh).cuda()
+        for wd, wref in ((torch.from_numpy(wh).cuda(), wh), (None, np.ones(n))):
+            for want_xtr in (True, False):
+                s, t, xr = eng.residual_sums(xd, yd, wd, coef, ybar, want_xtr)
+                ref_s = np.stack([(R ** 2).sum(0), (wref[:, None] * R ** 2).sum(0)], axis=1)
+                ref_t = np.array([((yh - ybar) ** 2).sum(), (wref * yh * yh).sum(), wref.sum(), yh.sum()])
+                assert np.abs(s - ref_s).max() <= 1e-11 * np.abs(ref_s).max(), (kernel, aligned, want_xtr)
+                assert np.abs(t - ref_t).max() <= 1e-11 * np.abs(ref_t).max()
+                if want_xtr:
+                    ref_x = (X.T @ R).T                      # [D+1, P]
+                    assert np.abs(xr - ref_x).max() <= 1e-11 * max(1.0, np.abs(ref_x).max()), (kernel, aligned)

@@ -43,43 +43,53 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                  : "d"(a), "d"(b));
 }
 
-// column c' (feature-major, augmented) of sample row: f = c' / (D+1), k = c' % (D+1); column P is y
+// Internal column layout (feature-major): feature f owns the DC columns f DC .. f DC + DC - 1 holding T_{K0} .. T_{K0 + DC - 1};
+// column P = F DC is y.  Two layouts:
+//   K0 = 0, DC = D + 1 (D = 0 only): every column of the reference's design matrix, W = P + 1 columns;
+//   K0 = 1, DC = D     (D >= 1):      the T_0 columns of the F features are F copies of the same all-ones column
+//       (DegreeOptimizer.py:96-119: transforms[0] = ones), so it is kept ONCE, as column P + 1: W = F D + 2 columns instead
+//       of F (D + 1) + 1 - at 79 features, degree 3: 239 instead of 317, 10 tiles of the upper triangle instead of 15.  The
+//       expand kernel below writes the full (F (D+1) + 1)^2 matrix of the C ABI from it (every entry of a T_0 row / column is
+//       the entry of the ones column).
 struct GramParams {
     const double* x;       // [n, F]
     const double* y;       // [n]
     double* partial;       // [S][n_tiles][TILE * TILE]
     long long n;
-    int F, D, P;           // P = F (D+1); augmented width P + 1
-    int T;                 // tiles per edge = ceil((P + 1) / TILE)
+    int F, D, DC, P;       // P = F DC = the y column
+    int W;                 // augmented width: P + 1 (+ 1 for the ones column when K0 = 1)
+    int T;                 // tiles per edge = ceil(W / TILE)
     int S;                 // sample slices
 };
 
 // fill one side's chunk: rows = samples s0 .. s0 + KC, columns c0 .. c0 + TILE of the augmented matrix.
-// D1T > 0: D + 1 is the compile-time constant D1T (unrolled recurrence, immediate store offsets).
-template <int MAXI, int D1T>
+// D1T > 0: the columns per feature DC are the compile-time constant D1T (unrolled recurrence, immediate store offsets).
+template <int MAXI, int D1T, int K0>
 __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI],
                                            int f_lo, int nf) {
     // item = (feature slot j, sample kk) with kk = t % 32 fastest: thread t handles slots t / 32, t / 32 + 4, ...;
     // the values were prefetched into xv[]
-    const int D1 = D1T > 0 ? D1T : p.D + 1;
+    const int D1 = D1T > 0 ? D1T : p.DC;
     const int kk = threadIdx.x & (KC - 1);
     const double lv = s0 + kk < p.n ? 1.0 : 0.0;         // rows beyond the slice are zero rows (last chunk only)
 #pragma unroll
     for (int it = 0; it < MAXI; ++it) {
         const int j = (threadIdx.x >> 5) + it * (GRAM_THREADS / KC);
         if (j > nf) break;
-        if (j == nf) {                                   // the y column (if this tile holds it) and the padding beyond P
+        if (j == nf) {                                   // the y column, the ones column (if this tile holds them), the padding
             const int cy = p.P - c0;
             if (cy >= 0 && cy < TILE) dst[cy * LDK + kk] = lv * xv[it];
-            for (int c = (cy >= 0 ? cy + 1 : 0); c < TILE; ++c)
-                if (c0 + c > p.P) dst[c * LDK + kk] = 0.0;
+            if (K0 && cy + 1 >= 0 && cy + 1 < TILE) dst[(cy + 1) * LDK + kk] = lv;
+            for (int c = (cy + 1 + K0 >= 0 ? cy + 1 + K0 : 0); c < TILE; ++c)
+                if (c0 + c >= p.W) dst[c * LDK + kk] = 0.0;
             continue;
         }
         const int f = f_lo + j;
         const double xc = clip_unit(xv[it]);
-        const int cbase = f * D1 - c0;                   // tile column of degree 0 of this feature
+        const int cbase = f * D1 - c0;                   // tile column of the feature's first column
         double* q = dst + cbase * LDK + kk;
         double t0 = lv, t1 = lv * xc;                    // T_0, T_1 (times the row's 0 / 1)
+        if (K0) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }      // first column = T_1
         if (cbase >= 0 && cbase + D1 <= TILE && f < p.F) {       // the feature's columns lie inside the tile: no checks
             q[0] = t0;
 #pragma unroll
@@ -110,10 +120,10 @@ __device__ __forceinline__ void fill_chunk(const GramParams& p, double* dst, lon
 #ifndef GRAM_FLAT_FILL
 #define GRAM_FLAT_FILL 1
 #endif
-template <int MAXI, int D1T>
+template <int MAXI, int D1T, int K0>
 __device__ __forceinline__ void fill_chunk_flat(const GramParams& p, double* dst, long long s0, int c0, const double (&xv)[MAXI],
                                                 int f_lo, int nf) {
-    const int D1 = D1T > 0 ? D1T : p.D + 1;
+    const int D1 = D1T > 0 ? D1T : p.DC;
     const int kk = threadIdx.x & (KC - 1), jrow = threadIdx.x >> 5;
     const double lv = s0 + kk < p.n ? 1.0 : 0.0;         // rows beyond the slice are zero rows (last chunk only)
 #pragma unroll
@@ -124,8 +134,10 @@ __device__ __forceinline__ void fill_chunk_flat(const GramParams& p, double* dst
         const int cbase = isy ? p.P - c0 : (f_lo + j) * D1 - c0;
         double* q = dst + cbase * LDK + kk;
         const double xc = clip_unit(v);
-        if ((feat || isy) && (unsigned)cbase < (unsigned)TILE) q[0] = isy ? lv * v : lv;
         double t0 = lv, t1 = lv * xc;
+        if (K0) { const double t2 = 2.0 * xc * t1 - t0; t0 = t1; t1 = t2; }      // first column = T_1
+        if ((feat || isy) && (unsigned)cbase < (unsigned)TILE) q[0] = isy ? lv * v : t0;
+        if (K0 && isy && (unsigned)(cbase + 1) < (unsigned)TILE) q[LDK] = lv;    // the ones column follows y
         if constexpr (D1T > 0) {
 #pragma unroll
             for (int k = 1; k < D1T; ++k) {
@@ -147,9 +159,9 @@ __device__ __forceinline__ void fill_chunk_flat(const GramParams& p, double* dst
 // a producer warp + mbarrier ring, cp.async input staging (round 2, first session), and chunks double buffered with the
 // production of chunk i + 1 sliced between the eight DMMA groups of chunk i (3 CTAs per SM: 3.55 ms against 3.49 ms);
 // 5 CTAs per SM at 96 registers (164 bytes spilled): 3.93 ms.
-// MAXI = most feature slots a thread fills per chunk and side: (64 / (D+1) + 2 features + the y slot) / 4
-template <int MAXI, int D1T>
-__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
+// MAXI = most feature slots a thread fills per chunk and side: (64 / DC + 2 features + the y slot) / 4
+template <int MAXI, int D1T, int K0>
+__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 6 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
     __shared__ __align__(16) double As[TILE * LDK];
     __shared__ __align__(16) double Bs[TILE * LDK];
     // upper-triangle tile (ti <= tj) from the linear tile index
@@ -158,8 +170,8 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
     const int tj = ti + rem;
     const bool diag = ti == tj;
     const int ca = ti * TILE, cb = tj * TILE;
-    const int D1 = p.D + 1;
-    // features touched by each side's 64 columns (+ one pseudo feature slot per sample: y / padding)
+    const int D1 = p.DC;
+    // features touched by each side's 64 columns (+ one pseudo feature slot per sample: y / ones / padding)
     const int fa_lo = ca / D1, fb_lo = cb / D1;
     auto nfeat = [&](int c0, int f_lo) {
         int c_hi = c0 + TILE - 1;
@@ -215,15 +227,15 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
     // degree: the branchy one (a run-time loop of predicated stores is slower: D = 8, 200 k rows: 4.86 against 5.70 ms)
     constexpr bool flat = GRAM_FLAT_FILL && D1T > 0;
     if constexpr (flat)
-        for (int i = threadIdx.x; i < TILE * LDK; i += GRAM_THREADS) As[i] = Bs[i] = 0.0;    // the columns beyond P stay zero
+        for (int i = threadIdx.x; i < TILE * LDK; i += GRAM_THREADS) As[i] = Bs[i] = 0.0;    // the columns beyond W stay zero
     for (long long s0 = s_begin; s0 < s_end; s0 += KC) {
         __syncthreads();                                 // the previous chunk's fragments are consumed
         if constexpr (flat) {
-            fill_chunk_flat<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
-            if (!diag) fill_chunk_flat<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
+            fill_chunk_flat<MAXI, D1T, K0>(q, As, s0, ca, xa, fa_lo, nfa);
+            if (!diag) fill_chunk_flat<MAXI, D1T, K0>(q, Bs, s0, cb, xb, fb_lo, nfb);
         } else {
-            fill_chunk<MAXI, D1T>(q, As, s0, ca, xa, fa_lo, nfa);
-            if (!diag) fill_chunk<MAXI, D1T>(q, Bs, s0, cb, xb, fb_lo, nfb);
+            fill_chunk<MAXI, D1T, K0>(q, As, s0, ca, xa, fa_lo, nfa);
+            if (!diag) fill_chunk<MAXI, D1T, K0>(q, Bs, s0, cb, xb, fb_lo, nfb);
         }
         __syncthreads();
         if (s0 + KC < s_end) {                           // next chunk's x / y: in flight during the MMAs
@@ -257,21 +269,19 @@ __global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 5 ? 3 : 4
         }
 }
 
-// sum the slices in a fixed order and scatter the tile into the degree-major (P+1) x (P+1) result (both triangles).
+// sum the slices in a fixed order into the W x W Gram matrix of the internal column layout (both triangles).
 // grid (tiles, TILE * TILE / blockDim): one element per thread, the slices read as coalesced 2 KB rows (a 15-CTA version that
 // walked a whole tile per CTA took 0.4 ms of the 4.07 ms Gram step).  Diagonal tiles contribute their upper triangle only
 // (the Gram kernel does not compute their strictly lower quadrant).
-__global__ void __launch_bounds__(256) qkan_cheb_gram_reduce_kernel(const double* __restrict__ partial, int n_tiles, int S, int T, int F, int D, int P,
-                                                                     double* __restrict__ G) {
+__global__ void __launch_bounds__(256) qkan_cheb_gram_reduce_kernel(const double* __restrict__ partial, int n_tiles, int S, int T, int W,
+                                                                     double* __restrict__ Gw) {
     const int tile = blockIdx.x;
     int ti = 0, rem = tile;
     while (rem >= T - ti) { rem -= T - ti; ++ti; }
     const int tj = ti + rem;
-    const int D1 = D + 1;
-    auto to_degree_major = [&](int c) { return c == P ? P : (c % D1) * F + c / D1; };
     const int e = blockIdx.y * blockDim.x + threadIdx.x;
     const int r = ti * TILE + e / TILE, c = tj * TILE + e % TILE;
-    if (r > P || c > P || (ti == tj && r > c)) return;
+    if (r >= W || c >= W || (ti == tj && r > c)) return;
     const double* src = partial + (size_t)tile * (TILE * TILE) + e;
     const size_t stride = (size_t)n_tiles * (TILE * TILE);
     double s = 0.0;
@@ -282,9 +292,24 @@ __global__ void __launch_bounds__(256) qkan_cheb_gram_reduce_kernel(const double
         s += v0; s += v1; s += v2; s += v3;
     }
     for (; q < S; ++q) s += src[(size_t)q * stride];
-    const int rr = to_degree_major(r), cc = to_degree_major(c);
-    G[(size_t)rr * (P + 1) + cc] = s;
-    G[(size_t)cc * (P + 1) + rr] = s;
+    Gw[(size_t)r * W + c] = s;
+    Gw[(size_t)c * W + r] = s;
+}
+
+// the (F (D+1) + 1)^2 result of the C ABI, columns in the reference's np.hstack order (k F + f, then y), from the internal
+// matrix: a T_k column with k < K0 is the ones column, the others sit at f DC + k - K0
+__global__ void __launch_bounds__(256) qkan_cheb_gram_expand_kernel(const double* __restrict__ Gw, int W, int F, int D, int DC, int K0,
+                                                                     double* __restrict__ G) {
+    const int PF = F * (D + 1);                              // the y row / column of the result
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)(PF + 1) * (PF + 1)) return;
+    const int rr = (int)(i / (PF + 1)), cc = (int)(i % (PF + 1));
+    auto internal = [&](int c) {
+        if (c == PF) return F * DC;
+        const int k = c / F, f = c - k * F;
+        return k < K0 ? F * DC + 1 : f * DC + (k - K0);
+    };
+    G[i] = Gw[(size_t)internal(rr) * W + internal(cc)];
 }
 
 // ---- residual pass: one warp per sample, lanes over features
@@ -800,22 +825,44 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace
 
-extern "C" int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes, int* slices) {
-    if (!bytes || n < 0 || F < 1 || D < 0 || D > MAX_D) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram_workspace: bad arguments");
-    const int P = F * (D + 1), T = (P + 1 + TILE - 1) / TILE, n_tiles = T * (T + 1) / 2;
+namespace {
+// internal layout of the Gram kernels for degree D (see GramParams)
+struct GramLayout {
+    int K0, DC, P, W, T, n_tiles;
+};
+GramLayout gram_layout(int F, int D) {
+    GramLayout g;
+    g.K0 = D >= 1 ? 1 : 0;
+    g.DC = D >= 1 ? D : 1;
+    g.P = F * g.DC;
+    g.W = g.P + 1 + g.K0;
+    g.T = (g.W + TILE - 1) / TILE;
+    g.n_tiles = g.T * (g.T + 1) / 2;
+    return g;
+}
+int gram_slices(int64_t n, int D, const GramLayout& g) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // eight whole waves of CTAs and not one CTA more (rounding up - 2 370 CTAs on 2 368 resident slots at 774 456 x 79,
     // D = 3 - left the SMs idle 15 % of the kernel while two stragglers ran a fifth wave; 4 waves 3.68 ms, 6: 3.55, 8: 3.49,
     // 12: 3.49), at least 8 chunks of samples per slice
-    const int per_sm = D >= 3 ? 4 : (D >= 1 ? 3 : 2);   // the launch bounds of qkan_cheb_gram_kernel<MAXI, .>
+    const int per_sm = D >= 3 ? 4 : (D == 2 ? 3 : 2);    // the launch bounds of qkan_cheb_gram_kernel<MAXI, ., .>
     int waves = 8;
     if (const char* e = getenv("QKAN_GRAM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;   // tuning aid
-    int S = waves * per_sm * sms / n_tiles;
+    int S = waves * per_sm * sms / g.n_tiles;
     const long long max_s = n / (8 * KC) > 0 ? n / (8 * KC) : 1;
     if (S > max_s) S = (int)max_s;
     if (S < 1) S = 1;
-    *bytes = (int64_t)S * n_tiles * TILE * TILE * (int64_t)sizeof(double);
+    return S;
+}
+}  // namespace
+
+extern "C" int qkan_cheb_gram_workspace(int64_t n, int F, int D, int64_t* bytes, int* slices) {
+    if (!bytes || n < 0 || F < 1 || D < 0 || D > MAX_D) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram_workspace: bad arguments");
+    const GramLayout g = gram_layout(F, D);
+    const int S = gram_slices(n, D, g);
+    // the slices' partial tiles, then the W x W matrix of the internal layout
+    *bytes = ((int64_t)S * g.n_tiles * TILE * TILE + (int64_t)g.W * g.W) * (int64_t)sizeof(double);
     if (slices) *slices = S;
     return QKAN_OK;
 }
@@ -830,25 +877,30 @@ extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F
     if (rc) return rc;
     if (workspace_bytes < need) return fail(QKAN_ERR_BAD_SHAPE, "qkan_cheb_gram: workspace too small (see qkan_cheb_gram_workspace)");
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    const GramLayout g = gram_layout(F, D);
     GramParams p;
-    p.x = x; p.y = y; p.partial = (double*)workspace; p.n = n; p.F = F; p.D = D; p.P = F * (D + 1);
-    p.T = (p.P + 1 + TILE - 1) / TILE;
+    p.x = x; p.y = y; p.partial = (double*)workspace; p.n = n; p.F = F; p.D = D; p.DC = g.DC; p.P = g.P; p.W = g.W;
+    p.T = g.T;
     p.S = S;
-    const int n_tiles = p.T * (p.T + 1) / 2;
-    const dim3 grid(n_tiles, S);
-    switch (D) {                                             // slots per side <= 64 / (D+1) + 2 features + y
-        case 0: qkan_cheb_gram_kernel<17, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 1: qkan_cheb_gram_kernel<9, 2><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 2: qkan_cheb_gram_kernel<9, 3><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 3: qkan_cheb_gram_kernel<5, 4><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 4: qkan_cheb_gram_kernel<5, 5><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        default: qkan_cheb_gram_kernel<5, 0><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+    double* Gw = p.partial + (size_t)S * g.n_tiles * TILE * TILE;
+    const dim3 grid(g.n_tiles, S);
+    switch (D) {                                             // slots per side <= 64 / DC + 2 features + the y slot
+        case 0: qkan_cheb_gram_kernel<17, 1, 0><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 1: qkan_cheb_gram_kernel<17, 1, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 2: qkan_cheb_gram_kernel<9, 2, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 3: qkan_cheb_gram_kernel<6, 3, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 4: qkan_cheb_gram_kernel<5, 4, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        default: qkan_cheb_gram_kernel<5, 0, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");
-    qkan_cheb_gram_reduce_kernel<<<dim3(n_tiles, TILE * TILE / 256), 256, 0, stream>>>(p.partial, n_tiles, S, p.T, F, D, p.P, G);
+    qkan_cheb_gram_reduce_kernel<<<dim3(g.n_tiles, TILE * TILE / 256), 256, 0, stream>>>(p.partial, g.n_tiles, S, g.T, g.W, Gw);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_reduce_kernel launch");
+    const long long full = (long long)(F * (D + 1) + 1) * (F * (D + 1) + 1);
+    qkan_cheb_gram_expand_kernel<<<(unsigned)((full + 255) / 256), 256, 0, stream>>>(Gw, g.W, F, D, g.DC, g.K0, G);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_expand_kernel launch");
     return QKAN_OK;
 }
 

@@ -49,7 +49,10 @@ def test_degree_abi_argument_errors_without_gpu():
     lib = b.lib()
     need, slices = ctypes.c_int64(), ctypes.c_int()
     assert lib.qkan_cheb_gram_workspace(774_456, 79, 3, ctypes.byref(need), ctypes.byref(slices)) == 0
-    assert need.value == slices.value * 15 * 64 * 64 * 8 and slices.value >= 1      # 5 x 5 tiles, upper triangle
+    # 79 x 3 + y + the ones column = 239 distinct columns: 4 x 4 tiles, upper triangle; then the 239 x 239 internal matrix
+    assert need.value == (slices.value * 10 * 64 * 64 + 239 * 239) * 8 and slices.value >= 1
+    assert lib.qkan_cheb_gram_workspace(1000, 5, 0, ctypes.byref(need), ctypes.byref(slices)) == 0
+    assert need.value == (slices.value * 1 * 64 * 64 + 6 * 6) * 8                  # degree 0: 5 columns + y
     assert lib.qkan_cheb_gram_workspace(100, 79, 17, ctypes.byref(need), None) == b.ERR_BAD_SHAPE   # D <= 16
     assert lib.qkan_cheb_gram(None, None, 10, 3, 2, None, None, 0, None) == b.ERR_BAD_SHAPE
     assert lib.qkan_cheb_residuals(None, None, None, 10, 3, 2, None, 0.0, None, None, None, None) == b.ERR_BAD_SHAPE

@@ -177,6 +177,7 @@ int qkan_simulate_circuit(const int* gates, const double* params, int n_gates, i
  *   leading F (d+1) block is X_d^T X_d for every d <= D, column P holds X_D^T y, and G[P][P] = y^T y.  Fused
  *   feature generation + FP64 tensor-core (DMMA) SYRK; partial tiles are summed in a fixed order, so the result is
  *   deterministic.  `workspace` (device) must hold qkan_cheb_gram_workspace() bytes.  0 <= D <= 16.
+ *   The F all-ones T_0 columns (DegreeOptimizer.py:96-119: transforms[0] = ones) are computed once; G is the full matrix.
  * qkan_cheb_residuals: explicit residuals r_d = y - X_d c_d of all D+1 fits in one pass.  coef [D+1][P] (device;
  *   zero where a column's degree exceeds d), w [n] sample weights or NULL, ybar = mean(y).  Per CTA c (count from
  *   qkan_cheb_residuals_ctas) partial sums, to be added up by the caller in CTA order:

@@ -12,9 +12,12 @@
 //     is already in flight; partial tiles are reduced in a fixed order (deterministic, no atomics).
 //     Internally columns are feature-major (f (D+1) + k) so that a 64-column tile reads only ~64 / (D+1)
 //     features of x; the result is written degree-major (k F + f), the reference's np.hstack order.
-//   * qkan_cheb_residual_kernel: the fits' explicit residuals r_d = y - X_d c_d for all d in one pass (one
-//     warp per sample), giving the sums behind the reference's MSE / R^2 (DegreeOptimizer.py:277-312) without
-//     the cancellation of y^T y - 2 c^T g + c^T G c, and X_D^T r_d for one step of iterative refinement.
+//     For D >= 1 the F identical all-ones T_0 columns are kept once (GramParams); the reduce kernel sums the slices
+//     into the matrix of the distinct columns and the expand kernel writes the full matrix of the C ABI from it.
+//   * qkan_cheb_residual_tile_kernel (D <= 4, F <= 128) / qkan_cheb_residual_kernel (any shape, one warp per
+//     sample): the fits' explicit residuals r_d = y - X_d c_d for all d in one pass, giving the sums behind the
+//     reference's MSE / R^2 (DegreeOptimizer.py:277-312) without the cancellation of y^T y - 2 c^T g + c^T G c,
+//     and X_D^T r_d for one step of iterative refinement.
 // The (D+1) small dense solves run on the host above the C ABI (numpy), as in the reference.
 #include "../../include/qkan_b200.h"
 

@@ -62,3 +62,58 @@ def test_host_logic_without_gpu(tmp_path):
     other = DegreeOptimizer([1, 1], 1)
     other.load_state(f, {'n_rows': 1, 'columns': [], 'sort_by': 'x'})
     assert other.network_shape == [5, 2] and other.max_degree == 3 and other.data_same is False
+
+
+def _design(x, D):
+    xc = np.clip(x, -1.0, 1.0)
+    T = [np.ones_like(xc), xc]
+    for _ in range(2, D + 1):
+        T.append(2.0 * xc * T[-1] - T[-2])
+    return np.hstack(T[:D + 1])
+
+
+@pytest.mark.parametrize("F,D", [(1, 0), (3, 1), (5, 3), (79, 3), (16, 4), (2, 8)])
+def test_nested_solver_returns_lstsq_minimum_norm_solutions(F, D):
+    """Host side of evaluate_degree (no GPU): from ONE Gram matrix of [X_D | y], _NestedSolver returns, for every degree d, what
+    np.linalg.lstsq(X_d, y) returns in the reference (DegreeOptimizer.py:146) - the minimum-norm solution of the rank-deficient
+    system (the T_0 columns of all features coincide), through one Cholesky factor of the reduced matrix."""
+    from qkan_implementation_b200.degree_optimizer import _NestedSolver, _blas_single_thread
+    rng = np.random.default_rng(100 * F + D)
+    n = 4000
+    x = rng.normal(0.0, 0.6, (n, F))
+    y = np.cos(2 * x[:, 0]) + 0.1 * rng.normal(size=n)
+    X = _design(x, D)
+    A = np.hstack([X, y[:, None]])
+    G = A.T @ A
+    P = F * (D + 1)
+    with _blas_single_thread():
+        solver = _NestedSolver(G, n, F, D)
+        assert solver.L is not None                          # well conditioned: the Cholesky path
+        for d in range(D + 1):
+            Pd = F * (d + 1)
+            got = solver.solve(d, G[:Pd, P])
+            ref = np.linalg.lstsq(X[:, :Pd], y, rcond=None)[0]
+            assert np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (d, np.abs(got - ref).max())
+
+
+def test_nested_solver_falls_back_on_duplicated_features():
+    """A duplicated feature makes the reduced Gram matrix singular: the solver must leave the Cholesky path and still return
+    lstsq's minimum-norm solution (eigen-decomposition of each leading block with lstsq's rank cut-off)."""
+    from qkan_implementation_b200.degree_optimizer import _NestedSolver
+    rng = np.random.default_rng(7)
+    n, F, D = 3000, 4, 2
+    x = rng.normal(0.0, 0.6, (n, F))
+    x[:, 3] = x[:, 1]
+    y = x[:, 0] ** 2 + 0.05 * rng.normal(size=n)
+    X = _design(x, D)
+    A = np.hstack([X, y[:, None]])
+    G = A.T @ A
+    P = F * (D + 1)
+    solver = _NestedSolver(G, n, F, D)
+    assert solver.L is None
+    for d in range(D + 1):
+        Pd = F * (d + 1)
+        got = solver.solve(d, G[:Pd, P])
+        ref = np.linalg.lstsq(X[:, :Pd], y, rcond=None)[0]
+        assert np.abs(X[:, :Pd] @ (got - ref)).max() <= 1e-7 * np.abs(y).max()      # the same fit
+        assert np.abs(got - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max())

@@ -482,6 +482,9 @@ __global__ void __launch_bounds__(RES_THREADS) qkan_cheb_residual_kernel(const d
 //   phase 2 (X^T r, only when requested): a warp per sample, a lane per feature as above, with the residuals of the
 //       sample broadcast from shared memory; the accumulators stay in registers for the whole launch.
 // Same outputs (per-CTA partial sums in the same layout) as the warp-per-sample kernel.
+// Measured and not kept: 64-sample tiles (SPL = 1) at 128 registers so that two CTAs share an SM and their passes overlap -
+// 0.286 / 0.204 ms against 0.294 / 0.194 ms (profiles/r03g_bench_residuals_two_ctas_rejected.jsonl): what the overlap gains, the
+// coefficient loads serving one sample instead of two lose.
 constexpr int RT_THREADS = 256;
 constexpr int RT_TS1 = 64;                                  // samples per tile and per phase-1 round (8 warps x 8 samples); tiles hold
                                                             // SPL rounds, SPL = 2 when two tiles of 128 samples fit shared memory
@@ -928,7 +931,8 @@ extern "C" int qkan_cheb_residuals(const double* x, const double* y, const doubl
         const int jf = (F + 31) / 32;
         // two rounds of 64 samples per tile (each coefficient load serves two samples per lane) when that fits shared memory
         const size_t tsmem2 = (size_t)rt_smem(F, D1, xtr != nullptr, 2 * RT_TS1).total * sizeof(double);
-        const int spl = tsmem2 <= 200 * 1024 ? 2 : 1;
+        int spl = tsmem2 <= 200 * 1024 ? 2 : 1;
+        if (const char* e = getenv("QKAN_RES_SPL")) spl = (atoi(e) == 2 && tsmem2 <= 200 * 1024) ? 2 : 1;   // A/B aid
         const size_t tsmem = spl == 2 ? tsmem2 : (size_t)rt_smem(F, D1, xtr != nullptr, RT_TS1).total * sizeof(double);
         const char* force = getenv("QKAN_RES_KERNEL");           // A/B aid: "warp" = the warp-per-sample kernel
         const bool warp_only = force && force[0] == 'w';

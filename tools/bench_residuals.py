@@ -39,11 +39,13 @@ def main():
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     results = {}
-    for kernel in ("tile", "warp"):
+    for kernel in ("tile", "tile_64_rows", "warp"):
+        os.environ.pop("QKAN_RES_KERNEL", None)
+        os.environ.pop("QKAN_RES_SPL", None)
         if kernel == "warp":
             os.environ["QKAN_RES_KERNEL"] = "warp"
-        else:
-            os.environ.pop("QKAN_RES_KERNEL", None)
+        elif kernel != "tile":
+            os.environ["QKAN_RES_SPL"] = "1"
         for want_xtr in (True, False):
             ts = []
             for _ in range(9):

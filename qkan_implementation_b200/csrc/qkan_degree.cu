@@ -163,8 +163,8 @@ __device__ __forceinline__ void fill_chunk_flat(const GramParams& p, double* dst
 // production of chunk i + 1 sliced between the eight DMMA groups of chunk i (3 CTAs per SM: 3.55 ms against 3.49 ms);
 // 5 CTAs per SM at 96 registers (164 bytes spilled): 3.93 ms.
 // MAXI = most feature slots a thread fills per chunk and side: (64 / DC + 2 features + the y slot) / 4
-template <int MAXI, int D1T, int K0>
-__global__ void __launch_bounds__(GRAM_THREADS, MAXI > 9 ? 2 : (MAXI > 6 ? 3 : 4)) qkan_cheb_gram_kernel(const GramParams p) {
+template <int MAXI, int D1T, int K0, int MINB = (MAXI > 9 ? 2 : (MAXI > 6 ? 3 : 4))>
+__global__ void __launch_bounds__(GRAM_THREADS, MINB) qkan_cheb_gram_kernel(const GramParams p) {
     __shared__ __align__(16) double As[TILE * LDK];
     __shared__ __align__(16) double Bs[TILE * LDK];
     // upper-triangle tile (ti <= tj) from the linear tile index
@@ -836,6 +836,19 @@ namespace {
 struct GramLayout {
     int K0, DC, P, W, T, n_tiles;
 };
+// resident CTAs per SM the Gram kernel is compiled for.  D = 3: three CTAs at 168 registers instead of four at 128 - under the
+// 128-register cap the straight-line producer recomputed the clip and the row's 0 / 1 several times per slot (583 instructions
+// per chunk between the two barriers; 330 at 168 registers): 2.71 -> 2.42 ms at 774 456 x 79 (profiles/r03h_gram_minb.jsonl).
+// QKAN_GRAM_MINB = 3 | 4 overrides it for D >= 3 (A/B aid).
+int gram_minb(int D) {
+    if (D < 3) return D == 2 ? 3 : 2;
+    int m = D == 3 ? 3 : 4;
+    if (const char* e = getenv("QKAN_GRAM_MINB")) {
+        const int v = atoi(e);
+        if (v == 3 || v == 4) m = v;
+    }
+    return m;
+}
 GramLayout gram_layout(int F, int D) {
     GramLayout g;
     g.K0 = D >= 1 ? 1 : 0;
@@ -852,7 +865,7 @@ int gram_slices(int64_t n, int D, const GramLayout& g) {
     // eight whole waves of CTAs and not one CTA more (rounding up - 2 370 CTAs on 2 368 resident slots at 774 456 x 79,
     // D = 3 - left the SMs idle 15 % of the kernel while two stragglers ran a fifth wave; 4 waves 3.68 ms, 6: 3.55, 8: 3.49,
     // 12: 3.49), at least 8 chunks of samples per slice
-    const int per_sm = D >= 3 ? 4 : (D == 2 ? 3 : 2);    // the launch bounds of qkan_cheb_gram_kernel<MAXI, ., .>
+    const int per_sm = gram_minb(D);                     // the launch bounds of qkan_cheb_gram_kernel<MAXI, ., ., MINB>
     int waves = 8;
     if (const char* e = getenv("QKAN_GRAM_WAVES")) waves = atoi(e) > 0 ? atoi(e) : waves;   // tuning aid
     int S = waves * per_sm * sms / g.n_tiles;
@@ -894,9 +907,18 @@ extern "C" int qkan_cheb_gram(const double* x, const double* y, int64_t n, int F
         case 0: qkan_cheb_gram_kernel<17, 1, 0><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
         case 1: qkan_cheb_gram_kernel<17, 1, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
         case 2: qkan_cheb_gram_kernel<9, 2, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 3: qkan_cheb_gram_kernel<6, 3, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        case 4: qkan_cheb_gram_kernel<5, 4, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
-        default: qkan_cheb_gram_kernel<5, 0, 1><<<grid, GRAM_THREADS, 0, stream>>>(p); break;
+        case 3:
+            if (gram_minb(D) == 3) qkan_cheb_gram_kernel<6, 3, 1, 3><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            else qkan_cheb_gram_kernel<6, 3, 1, 4><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            break;
+        case 4:
+            if (gram_minb(D) == 3) qkan_cheb_gram_kernel<5, 4, 1, 3><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            else qkan_cheb_gram_kernel<5, 4, 1, 4><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            break;
+        default:
+            if (gram_minb(D) == 3) qkan_cheb_gram_kernel<5, 0, 1, 3><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            else qkan_cheb_gram_kernel<5, 0, 1, 4><<<grid, GRAM_THREADS, 0, stream>>>(p);
+            break;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "qkan_cheb_gram_kernel launch");

@@ -279,3 +279,22 @@ def test_sharded_degree_evaluation_gloo_world2(weighted):
     assert all(ok for _, ok, _, _, _ in res), res
     assert [r[2] for r in res] == [1501, 1501] and sum(r[3] for r in res) == 1501
     assert res[0][4] == res[1][4]                                     # both ranks hold the same scores
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_degree_solve_host_logic_single_process(weighted):
+    """ChebyshevLeastSquares.solve without a process group (one packed download per residual pass, nested Cholesky solves,
+    one refinement step), kernels replaced by their oracle: scores and R^2 of the reference algorithm."""
+    from oracle import degree_oracle as do
+    from qkan_implementation_b200.degree_optimizer import ChebyshevLeastSquares
+    n, F, D = 2003, 7, 3
+    rng = np.random.default_rng(5)
+    x = rng.normal(0, 0.6, (n, F))
+    y = np.cos(2 * x[:, 0]) + 0.3 * x[:, 1] ** 3 + 0.05 * rng.normal(size=n)
+    w = rng.uniform(0.5, 2, n) if weighted else None
+    eng = ChebyshevLeastSquares(D, kernels=_OracleKernels())
+    scores, r2 = eng.solve(x, y, w)
+    ref_s, ref_r = do.evaluate_degree(x, y, D, w)
+    assert np.abs(scores - ref_s).max() <= 1e-12 * ref_s.max()
+    assert np.abs(r2 - ref_r).max() <= 1e-9 * max(1, np.abs(ref_r).max())
+    assert eng.last["rows"] == n and eng.last["coef"].shape == (D + 1, F * (D + 1))
